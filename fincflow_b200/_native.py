@@ -1,0 +1,192 @@
+"""ctypes binding of libfincflow_b200.so (include/fincflow_b200.h) for torch tensors.
+
+PyTorch is plumbing here: it owns device memory and streams; every kernel on the FInC hot
+path is our own sm_100a code behind the C ABI.  There is NO CPU fallback: a missing
+library or a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfincflow_b200.so")
+
+ORDER_CODE = {"TL": 0, "TR": 1, "BL": 2, "BR": 3}
+ORDERS_UNIT = 0xE4  # TL | TR<<2 | BL<<4 | BR<<6   (fastflow/fastflow.py:24-27)
+
+FLAG_NAIVE = 1
+FLAG_NO_MASK = 2
+FLAG_ACCUMULATE = 4
+
+# every symbol declared in include/fincflow_b200.h
+SYMBOLS = (
+    "finc_abi_version", "finc_error_string", "finc_set_device", "finc_sm_count",
+    "finc_forward_f32", "finc_backward_input_f32", "finc_backward_weight_workspace_bytes",
+    "finc_backward_weight_f32", "finc_inverse_f32", "finc_apply_grad_mask_f32", "finc_logdet_f32",
+)
+
+_lib = None
+_tls = threading.local()
+
+
+class FincNativeError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library; fails loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FincNativeError(
+            f"{LIB_PATH} is missing: build it with `python -m fincflow_b200.build` "
+            "(or __graft_entry__.build()).  fincflow_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    i, u, p, sz = ctypes.c_int, ctypes.c_uint, ctypes.c_void_p, ctypes.c_size_t
+    dims = [i] * 7
+    lib.finc_abi_version.restype = i
+    lib.finc_error_string.restype = ctypes.c_char_p
+    lib.finc_error_string.argtypes = [i]
+    lib.finc_set_device.argtypes = [i]
+    lib.finc_sm_count.restype = i
+    lib.finc_forward_f32.argtypes = [p, p, p, p, *dims, u, u, p]
+    lib.finc_backward_input_f32.argtypes = [p, p, p, *dims, u, u, p]
+    lib.finc_backward_weight_workspace_bytes.restype = sz
+    lib.finc_backward_weight_workspace_bytes.argtypes = dims
+    lib.finc_backward_weight_f32.argtypes = [p, p, p, p, sz, *dims, u, u, p]
+    lib.finc_inverse_f32.argtypes = [p, p, p, *dims, u, u, p]
+    lib.finc_apply_grad_mask_f32.argtypes = [p, i, i, i, i, u, p]
+    lib.finc_logdet_f32.argtypes = [p, p, *dims, u, p]
+    for f in ("finc_set_device", "finc_forward_f32", "finc_backward_input_f32", "finc_backward_weight_f32",
+              "finc_inverse_f32", "finc_apply_grad_mask_f32", "finc_logdet_f32"):
+        getattr(lib, f).restype = i
+    if lib.finc_abi_version() != 1:
+        raise FincNativeError("libfincflow_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def pack_orders(orders) -> int:
+    v = 0
+    for g, o in enumerate(orders):
+        v |= (ORDER_CODE[o] if isinstance(o, str) else int(o)) << (2 * g)
+    return v
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load().finc_error_string(rc).decode()
+        raise FincNativeError(f"{what} failed: {msg} (code {rc})")
+
+
+def _prep(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise FincNativeError(f"{name} must be a CUDA tensor: fincflow_b200 has no CPU path")
+    if t.dtype != torch.float32:
+        raise FincNativeError(f"{name} must be float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _bind_device(t: torch.Tensor):
+    dev = t.device.index
+    if getattr(_tls, "device", None) != dev:
+        _check(load().finc_set_device(dev), "finc_set_device")
+        _tls.device = dev
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _dims(x: torch.Tensor, w: torch.Tensor, G: int):
+    B, CT, H, W = x.shape
+    if CT % G != 0:
+        raise FincNativeError(f"channels {CT} not divisible by groups {G}")
+    C = CT // G
+    if tuple(w.shape[:2]) != (G * C, C):
+        raise FincNativeError(f"weight shape {tuple(w.shape)} does not match [G*C={G * C}, C={C}, kH, kW]")
+    return B, G, C, H, W, int(w.shape[2]), int(w.shape[3])
+
+
+def forward(x, w, G=4, orders=ORDERS_UNIT, want_logdet=True, flags=0):
+    """z, logdet[B] (or None).  C ABI: finc_forward_f32."""
+    x, w = _prep(x, "x"), _prep(w, "weight")
+    d = _dims(x, w, G)
+    _bind_device(x)
+    z = torch.empty_like(x)
+    logdet = torch.empty(d[0], dtype=torch.float32, device=x.device) if want_logdet else None
+    _check(load().finc_forward_f32(x.data_ptr(), w.data_ptr(), z.data_ptr(),
+                                   logdet.data_ptr() if want_logdet else None,
+                                   *d, orders, flags, _stream(x)), "finc_forward_f32")
+    return z, logdet
+
+
+def backward_input(dz, w, G=4, orders=ORDERS_UNIT, flags=0):
+    dz, w = _prep(dz, "dz"), _prep(w, "weight")
+    d = _dims(dz, w, G)
+    _bind_device(dz)
+    dx = torch.empty_like(dz)
+    _check(load().finc_backward_input_f32(dz.data_ptr(), w.data_ptr(), dx.data_ptr(), *d, orders, flags,
+                                          _stream(dz)), "finc_backward_input_f32")
+    return dx
+
+
+def backward_weight(dz, x, ksize, G=4, orders=ORDERS_UNIT, flags=0, out=None):
+    """Masked dW [G*C, C, kH, kW] (FLAG_NO_MASK for the raw gradient).  `out` may be a view
+    into a flat gradient bucket; FLAG_ACCUMULATE adds into it."""
+    dz, x = _prep(dz, "dz"), _prep(x, "x")
+    B, CT, H, W = x.shape
+    C = CT // G
+    kH, kW = ksize
+    _bind_device(x)
+    if out is None:
+        out = torch.empty((G * C, C, kH, kW), dtype=torch.float32, device=x.device)
+    elif not (out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and out.numel() == G * C * C * kH * kW):
+        raise FincNativeError("backward_weight: `out` must be a contiguous float32 CUDA tensor of G*C*C*kH*kW elements")
+    lib = load()
+    nbytes = lib.finc_backward_weight_workspace_bytes(B, G, C, H, W, kH, kW)
+    ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=x.device)
+    _check(lib.finc_backward_weight_f32(dz.data_ptr(), x.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                        B, G, C, H, W, kH, kW, orders, flags, _stream(x)),
+           "finc_backward_weight_f32")
+    return out
+
+
+def inverse(z, w, G=4, orders=ORDERS_UNIT, flags=0, out=None):
+    z, w = _prep(z, "z"), _prep(w, "weight")
+    d = _dims(z, w, G)
+    _bind_device(z)
+    x = torch.empty_like(z) if out is None else out
+    _check(load().finc_inverse_f32(z.data_ptr(), w.data_ptr(), x.data_ptr(), *d, orders, flags, _stream(z)),
+           "finc_inverse_f32")
+    return x
+
+
+def apply_grad_mask_(dw, G, orders):
+    if not dw.is_contiguous():
+        raise FincNativeError("apply_grad_mask_: dw must be contiguous (in-place operation)")
+    dw = _prep(dw, "dw")
+    _bind_device(dw)
+    C, kH, kW = int(dw.shape[1]), int(dw.shape[2]), int(dw.shape[3])
+    _check(load().finc_apply_grad_mask_f32(dw.data_ptr(), G, C, kH, kW, orders, _stream(dw)),
+           "finc_apply_grad_mask_f32")
+    return dw
+
+
+def logdet(w, B, H, W, G=4, orders=ORDERS_UNIT):
+    w = _prep(w, "weight")
+    _bind_device(w)
+    C, kH, kW = int(w.shape[1]), int(w.shape[2]), int(w.shape[3])
+    out = torch.empty(B, dtype=torch.float32, device=w.device)
+    _check(load().finc_logdet_f32(w.data_ptr(), out.data_ptr(), B, G, C, H, W, kH, kW, orders, _stream(w)),
+           "finc_logdet_f32")
+    return out
+
+
+def sm_count() -> int:
+    return load().finc_sm_count()

@@ -1,0 +1,161 @@
+// finc_api.cu -- extern "C" entry points declared in include/fincflow_b200.h.
+//
+// Argument checking + dispatch: tiled sm_100a kernels when the shape is covered, generic
+// GPU kernels otherwise.  There is no CPU path.
+#include "finc_common.cuh"
+
+namespace finc {
+
+static int g_sm_count[64];
+static size_t g_smem_optin[64];
+
+static int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    return dev < 0 || dev >= 64 ? 0 : dev;
+}
+
+int sm_count_cached() {
+    const int dev = current_device();
+    if (g_sm_count[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        g_sm_count[dev] = v;
+    }
+    return g_sm_count[dev];
+}
+
+size_t max_optin_smem_cached() {
+    const int dev = current_device();
+    if (g_smem_optin[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || v <= 0)
+            v = 48 * 1024;
+        g_smem_optin[dev] = (size_t)v;
+    }
+    return g_smem_optin[dev];
+}
+
+static bool shape_ok(int B, int G, int C, int H, int W, int kH, int kW) {
+    return B >= 0 && G >= 1 && G <= 16 && C >= 1 && H >= 1 && W >= 1 && kH >= 1 && kW >= 1 &&
+           (long)G * C <= (1L << 20) && (long)H * W <= (1L << 28);
+}
+
+static Shape mk(int B, int G, int C, int H, int W, int kH, int kW, unsigned orders) {
+    Shape s;
+    s.B = B; s.G = G; s.C = C; s.H = H; s.W = W; s.kH = kH; s.kW = kW; s.orders = orders;
+    return s;
+}
+
+}  // namespace finc
+
+using namespace finc;
+
+extern "C" {
+
+int finc_abi_version(void) { return FINC_ABI_VERSION; }
+
+const char* finc_error_string(int code) {
+    switch (code) {
+        case FINC_OK: return "ok";
+        case FINC_E_BADARG: return "finc: bad argument (null pointer, non-positive dimension or G > 16)";
+        case FINC_E_WORKSPACE: return "finc: workspace too small (see finc_backward_weight_workspace_bytes)";
+        case FINC_E_UNSUPPORTED: return "finc: unsupported configuration";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "finc: unknown error";
+    }
+}
+
+int finc_set_device(int device) { return (int)cudaSetDevice(device); }
+
+int finc_sm_count(void) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    return v;
+}
+
+int finc_forward_f32(const float* x, const float* w, float* z, float* logdet, int B, int G, int C, int H, int W,
+                     int kH, int kW, unsigned orders, unsigned flags, void* stream) {
+    if (!shape_ok(B, G, C, H, W, kH, kW) || !w) return FINC_E_BADARG;
+    if (B == 0) return FINC_OK;
+    if (!x || !z || x == z) return FINC_E_BADARG;
+    const Shape s = mk(B, G, C, H, W, kH, kW, orders);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = 0;
+    bool handled = false;
+    if (!(flags & FINC_FLAG_NAIVE)) rc = launch_conv_fast(x, w, z, logdet, s, false, st, &handled);
+    if (rc) return rc;
+    if (handled) return FINC_OK;  // logdet was written by the fused epilogue
+    rc = launch_conv_naive(x, w, z, s, false, st);
+    if (rc) return rc;
+    if (logdet) rc = launch_logdet(w, logdet, s, st);
+    return rc;
+}
+
+int finc_backward_input_f32(const float* dz, const float* w, float* dx, int B, int G, int C, int H, int W, int kH,
+                            int kW, unsigned orders, unsigned flags, void* stream) {
+    if (!shape_ok(B, G, C, H, W, kH, kW) || !w) return FINC_E_BADARG;
+    if (B == 0) return FINC_OK;
+    if (!dz || !dx || dz == dx) return FINC_E_BADARG;
+    const Shape s = mk(B, G, C, H, W, kH, kW, orders);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = 0;
+    bool handled = false;
+    if (!(flags & FINC_FLAG_NAIVE)) rc = launch_conv_fast(dz, w, dx, nullptr, s, true, st, &handled);
+    if (rc) return rc;
+    if (!handled) rc = launch_conv_naive(dz, w, dx, s, true, st);
+    return rc;
+}
+
+size_t finc_backward_weight_workspace_bytes(int B, int G, int C, int H, int W, int kH, int kW) {
+    if (!shape_ok(B, G, C, H, W, kH, kW)) return 0;
+    return wgrad_workspace_floats(mk(B, G, C, H, W, kH, kW, 0)) * sizeof(float);
+}
+
+int finc_backward_weight_f32(const float* dz, const float* x, float* dw, void* workspace, size_t workspace_bytes,
+                             int B, int G, int C, int H, int W, int kH, int kW, unsigned orders, unsigned flags,
+                             void* stream) {
+    if (!shape_ok(B, G, C, H, W, kH, kW) || !dw) return FINC_E_BADARG;
+    const Shape s = mk(B, G, C, H, W, kH, kW, orders);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B > 0 && (!dz || !x)) return FINC_E_BADARG;
+    int rc = 0;
+    bool handled = false;
+    if (!(flags & FINC_FLAG_NAIVE) && B > 0) {
+        if (!workspace) return FINC_E_WORKSPACE;
+        rc = launch_wgrad_fast(dz, x, dw, (float*)workspace, workspace_bytes / sizeof(float), s, flags, st, &handled);
+        if (rc) return rc;
+    }
+    if (!handled) rc = launch_wgrad_naive(dz, x, dw, s, flags, st);  // B == 0 writes zeros
+    return rc;
+}
+
+int finc_inverse_f32(const float* z, const float* w, float* x, int B, int G, int C, int H, int W, int kH, int kW,
+                     unsigned orders, unsigned flags, void* stream) {
+    if (!shape_ok(B, G, C, H, W, kH, kW) || !w) return FINC_E_BADARG;
+    if (B == 0) return FINC_OK;
+    if (!z || !x) return FINC_E_BADARG;
+    const Shape s = mk(B, G, C, H, W, kH, kW, orders);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = 0;
+    bool handled = false;
+    if (!(flags & FINC_FLAG_NAIVE)) rc = launch_inverse_fast(z, w, x, s, st, &handled);
+    if (rc) return rc;
+    if (!handled) rc = launch_inverse_naive(z, w, x, s, st);
+    return rc;
+}
+
+int finc_apply_grad_mask_f32(float* dw, int G, int C, int kH, int kW, unsigned orders, void* stream) {
+    if (!shape_ok(1, G, C, 1, 1, kH, kW) || !dw) return FINC_E_BADARG;
+    return launch_mask(dw, mk(1, G, C, 1, 1, kH, kW, orders), (cudaStream_t)stream);
+}
+
+int finc_logdet_f32(const float* w, float* logdet, int B, int G, int C, int H, int W, int kH, int kW,
+                    unsigned orders, void* stream) {
+    if (!shape_ok(B, G, C, H, W, kH, kW) || !w) return FINC_E_BADARG;
+    if (B == 0) return FINC_OK;
+    if (!logdet) return FINC_E_BADARG;
+    return launch_logdet(w, logdet, mk(B, G, C, H, W, kH, kW, orders), (cudaStream_t)stream);
+}
+
+}  // extern "C"

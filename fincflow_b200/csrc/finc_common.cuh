@@ -1,0 +1,109 @@
+// finc_common.cuh -- shared device helpers for the sm_100a FInC kernels.
+//
+// Data model (see include/fincflow_b200.h): fp32 NCHW [B, G*C, H, W]; tile (n, g) is the
+// contiguous block of C*H*W floats at ((n*G + g) * C*H*W).  Because a tile is contiguous
+// it is moved global<->shared with 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP)
+// completing on an mbarrier -- no tensor map needed.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fincflow_b200.h"
+
+namespace finc {
+
+struct Shape {
+    int B, G, C, H, W, kH, kW;
+    unsigned orders;
+};
+
+__host__ __device__ __forceinline__ int order_of(unsigned orders, int g) { return (orders >> (2 * g)) & 3; }
+// tap (a,b) reads x[h + row_off(a)][w + col_off(b)]   (reference: layers/conv.py:41-55)
+__host__ __device__ __forceinline__ int row_off(int order, int a, int kH) { return (order & 2) ? a : a - (kH - 1); }
+__host__ __device__ __forceinline__ int col_off(int order, int b, int kW) { return (order & 1) ? b : b - (kW - 1); }
+__host__ __device__ __forceinline__ int corner_a(int order, int kH) { return (order & 2) ? 0 : kH - 1; }
+__host__ __device__ __forceinline__ int corner_b(int order, int kW) { return (order & 1) ? 0 : kW - 1; }
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + 1-D bulk async copies (TMA engine, no descriptor).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// generic-proxy accesses to shared memory -> visible to / ordered before the async proxy (TMA)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// try_wait suspends the thread in hardware for a bounded time; the spin bound turns a
+// protocol bug into a trap (launch error) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        if (spins > (1u << 24)) __trap();
+    }
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+// shared -> global bulk copy (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until all committed bulk stores have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ bool is_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---------------------------------------------------------------------------------------
+// host-side launch helpers (defined in finc_api.cu)
+// ---------------------------------------------------------------------------------------
+int sm_count_cached();
+size_t max_optin_smem_cached();
+
+// launchers implemented by the per-kernel translation units; all return cudaError_t as int
+int launch_conv_fast(const float* x, const float* w, float* y, float* logdet, const Shape& s, bool transpose,
+                     cudaStream_t st, bool* handled);
+int launch_inverse_fast(const float* z, const float* w, float* x, const Shape& s, cudaStream_t st, bool* handled);
+int launch_wgrad_fast(const float* dz, const float* x, float* dw, float* workspace, size_t ws_floats, const Shape& s,
+                      unsigned flags, cudaStream_t st, bool* handled);
+size_t wgrad_workspace_floats(const Shape& s);
+
+int launch_conv_naive(const float* x, const float* w, float* y, const Shape& s, bool transpose, cudaStream_t st);
+int launch_inverse_naive(const float* z, const float* w, float* x, const Shape& s, cudaStream_t st);
+int launch_wgrad_naive(const float* dz, const float* x, float* dw, const Shape& s, unsigned flags, cudaStream_t st);
+int launch_mask(float* dw, const Shape& s, cudaStream_t st);
+int launch_logdet(const float* w, float* logdet, const Shape& s, cudaStream_t st);
+
+}  // namespace finc

@@ -1,0 +1,198 @@
+// finc_naive.cu -- generic kernels: any C, kernel size, image size, alignment.
+//
+// These are the universal fall-back for shapes the tiled kernels do not cover (tiles larger
+// than shared memory, exotic kernel sizes) and the on-device cross-check used by the tests
+// (FINC_FLAG_NAIVE).  They are still GPU code: there is no CPU fallback anywhere.
+#include "finc_common.cuh"
+
+namespace finc {
+
+// one thread per output element, grid-stride.  transpose=false: forward
+// (reference layers/conv.py:102-107); transpose=true: backward wrt input.
+__global__ void conv_naive_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
+                                  Shape s, bool transpose) {
+    const long HW = (long)s.H * s.W;
+    const long total = (long)s.B * s.G * s.C * HW;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int ww = (int)(e % s.W);
+        const int h = (int)((e / s.W) % s.H);
+        const int oc = (int)((e / HW) % s.C);
+        const long tile = e / (HW * s.C);  // n*G + g
+        const int g = (int)(tile % s.G);
+        const int ord = order_of(s.orders, g);
+        const float* xt = x + tile * s.C * HW;
+        const float* wg = w + (long)g * s.C * s.C * s.kH * s.kW;
+        float acc = 0.f;
+        for (int ic = 0; ic < s.C; ++ic)
+            for (int a = 0; a < s.kH; ++a) {
+                const int ro = row_off(ord, a, s.kH);
+                const int hh = transpose ? h - ro : h + ro;
+                if (hh < 0 || hh >= s.H) continue;
+                for (int b = 0; b < s.kW; ++b) {
+                    const int co = col_off(ord, b, s.kW);
+                    const int wc = transpose ? ww - co : ww + co;
+                    if (wc < 0 || wc >= s.W) continue;
+                    const float wv = transpose ? wg[((ic * s.C + oc) * s.kH + a) * s.kW + b]
+                                               : wg[((oc * s.C + ic) * s.kH + a) * s.kW + b];
+                    acc = fmaf(wv, xt[ic * HW + hh * s.W + wc], acc);
+                }
+            }
+        y[e] = acc;
+    }
+}
+
+// one CTA per tile (n,g); anti-diagonal wavefront with two block barriers per diagonal,
+// operating in place on the output in global memory.
+// reference: utils/fastflow_cuda_inverse/cinc_cuda_kernel_level2.cu:49-72,98-132.
+__global__ void inverse_naive_kernel(const float* z, const float* __restrict__ w, float* x, Shape s) {
+    const long HW = (long)s.H * s.W;
+    const int H = s.H, W = s.W, C = s.C, kH = s.kH, kW = s.kW;
+    for (long tile = blockIdx.x; tile < (long)s.B * s.G; tile += gridDim.x) {
+        const int g = (int)(tile % s.G);
+        const int ord = order_of(s.orders, g);
+        const bool bot = ord & 2, right = ord & 1;
+        const float* zt = z + tile * C * HW;
+        volatile float* xt = x + tile * C * HW;
+        const float* wg = w + (long)g * C * C * kH * kW;
+        const int ca = corner_a(ord, kH), cb = corner_b(ord, kW);
+        for (int d = 0; d < H + W - 1; ++d) {
+            const int hs_lo = max(0, d - (W - 1));
+            const int hs_hi = min(H - 1, d);
+            const int npix = hs_hi - hs_lo + 1;
+            // phase A: everything except the corner tap (depends on earlier diagonals only)
+            for (int it = threadIdx.x; it < npix * C; it += blockDim.x) {
+                const int o = it % C;
+                const int hs = hs_lo + it / C, ws = d - hs;
+                const int h = bot ? H - 1 - hs : hs, ww = right ? W - 1 - ws : ws;
+                float acc = zt[o * HW + h * W + ww];
+                for (int k_h = 0; k_h < kH && k_h <= hs; ++k_h) {
+                    const int hh = bot ? h + k_h : h - k_h;
+                    const int a = bot ? k_h : kH - 1 - k_h;
+                    for (int k_w = 0; k_w < kW && k_w <= ws; ++k_w) {
+                        if (k_h == 0 && k_w == 0) continue;
+                        const int wc = right ? ww + k_w : ww - k_w;
+                        const int b = right ? k_w : kW - 1 - k_w;
+                        for (int i = 0; i < C; ++i)
+                            acc = fmaf(-xt[i * HW + hh * W + wc], wg[((o * C + i) * kH + a) * kW + b], acc);
+                    }
+                }
+                xt[o * HW + h * W + ww] = acc;
+            }
+            __syncthreads();
+            // phase B: channel-triangular corner tap, sequential in o inside one thread
+            for (int p = threadIdx.x; p < npix; p += blockDim.x) {
+                const int hs = hs_lo + p, ws = d - hs;
+                const int h = bot ? H - 1 - hs : hs, ww = right ? W - 1 - ws : ws;
+                for (int o = 1; o < C; ++o) {
+                    float acc = xt[o * HW + h * W + ww];
+                    for (int i = 0; i < o; ++i)
+                        acc = fmaf(-xt[i * HW + h * W + ww], wg[((o * C + i) * kH + ca) * kW + cb], acc);
+                    xt[o * HW + h * W + ww] = acc;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// one warp per dw element; lanes stride over (n,h,w); shuffle reduction (deterministic).
+__global__ void wgrad_naive_kernel(const float* __restrict__ dz, const float* __restrict__ x, float* __restrict__ dw,
+                                   Shape s, unsigned flags) {
+    const int lane = threadIdx.x & 31;
+    const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    const long nout = (long)s.G * s.C * s.C * s.kH * s.kW;
+    const long HW = (long)s.H * s.W;
+    for (long e = warp; e < nout; e += nwarps) {
+        const int b = (int)(e % s.kW);
+        const int a = (int)((e / s.kW) % s.kH);
+        const int i = (int)((e / (s.kW * s.kH)) % s.C);
+        const int o = (int)((e / ((long)s.kW * s.kH * s.C)) % s.C);
+        const int g = (int)(e / ((long)s.kW * s.kH * s.C * s.C));
+        const int ord = order_of(s.orders, g);
+        const int ro = row_off(ord, a, s.kH), co = col_off(ord, b, s.kW);
+        float acc = 0.f;
+        for (long p = lane; p < (long)s.B * HW; p += 32) {
+            const int ww = (int)(p % s.W);
+            const int h = (int)((p / s.W) % s.H);
+            const long n = p / HW;
+            const int hh = h + ro, wc = ww + co;
+            if (hh < 0 || hh >= s.H || wc < 0 || wc >= s.W) continue;
+            acc = fmaf(dz[((n * s.G + g) * s.C + o) * HW + h * s.W + ww], x[((n * s.G + g) * s.C + i) * HW + hh * s.W + wc],
+                       acc);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) {
+            const bool masked = !(flags & FINC_FLAG_NO_MASK) && a == corner_a(ord, s.kH) && b == corner_b(ord, s.kW) && i >= o;
+            if (masked) acc = 0.f;
+            if (flags & FINC_FLAG_ACCUMULATE) acc += dw[e];
+            dw[e] = acc;
+        }
+    }
+}
+
+// PaddedConv2d.reset_gradients (layers/conv.py:98-99) without the H2D mask copy.
+__global__ void mask_kernel(float* dw, Shape s) {
+    const int total = s.G * s.C * s.C;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int i = e % s.C, o = (e / s.C) % s.C, g = e / (s.C * s.C);
+        if (i < o) continue;
+        const int ord = order_of(s.orders, g);
+        dw[(((long)g * s.C + o) * s.C + i) * s.kH * s.kW + corner_a(ord, s.kH) * s.kW + corner_b(ord, s.kW)] = 0.f;
+    }
+}
+
+// logdet[n] = H*W*sum log|diag corner tap|; one CTA, fixed-order reduction.
+__global__ void logdet_kernel(const float* __restrict__ w, float* __restrict__ logdet, Shape s) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (int e = threadIdx.x; e < s.G * s.C; e += blockDim.x) {
+        const int o = e % s.C, g = e / s.C;
+        const int ord = order_of(s.orders, g);
+        acc += logf(fabsf(w[(((long)g * s.C + o) * s.C + o) * s.kH * s.kW + corner_a(ord, s.kH) * s.kW + corner_b(ord, s.kW)]));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+    tot *= (float)s.H * (float)s.W;
+    for (int n = threadIdx.x; n < s.B; n += blockDim.x) logdet[n] = tot;
+}
+
+int launch_conv_naive(const float* x, const float* w, float* y, const Shape& s, bool transpose, cudaStream_t st) {
+    const long total = (long)s.B * s.G * s.C * s.H * s.W;
+    const int threads = 256;
+    const long blocks = (total + threads - 1) / threads;
+    conv_naive_kernel<<<(unsigned)(blocks > 148L * 64 ? 148L * 64 : blocks), threads, 0, st>>>(x, w, y, s, transpose);
+    return (int)cudaGetLastError();
+}
+
+int launch_inverse_naive(const float* z, const float* w, float* x, const Shape& s, cudaStream_t st) {
+    const long tiles = (long)s.B * s.G;
+    inverse_naive_kernel<<<(unsigned)(tiles > 148L * 32 ? 148L * 32 : tiles), 128, 0, st>>>(z, w, x, s);
+    return (int)cudaGetLastError();
+}
+
+int launch_wgrad_naive(const float* dz, const float* x, float* dw, const Shape& s, unsigned flags, cudaStream_t st) {
+    const long nout = (long)s.G * s.C * s.C * s.kH * s.kW;
+    const int threads = 256;
+    const long blocks = (nout * 32 + threads - 1) / threads;
+    wgrad_naive_kernel<<<(unsigned)(blocks > 148L * 32 ? 148L * 32 : blocks), threads, 0, st>>>(dz, x, dw, s, flags);
+    return (int)cudaGetLastError();
+}
+
+int launch_mask(float* dw, const Shape& s, cudaStream_t st) {
+    const int total = s.G * s.C * s.C;
+    mask_kernel<<<(total + 255) / 256, 256, 0, st>>>(dw, s);
+    return (int)cudaGetLastError();
+}
+
+int launch_logdet(const float* w, float* logdet, const Shape& s, cudaStream_t st) {
+    logdet_kernel<<<1, 256, 0, st>>>(w, logdet, s);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace finc

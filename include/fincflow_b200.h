@@ -1,0 +1,122 @@
+/*
+ * fincflow_b200.h -- C ABI of the B200-native FInC invertible k x k convolution hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry
+ * point names the reference interface it replaces (paths relative to the reference repo
+ * aditya-v-kallappa/FInCFlow).  The reference's native interface for this path is a
+ * JIT-built pybind11 module with one function
+ *     inverse(input[B,4Cq,H,W], kernel[4Cq,Cq,kH,kW], output zero-filled) -> [output]
+ * (fastflow/utils/fastflow_cuda_inverse/cinc_cuda_level2.cpp:19-32, call site
+ * fastflow/fastflow.py:91-92); forward / backward go through F.pad + nn.Conv2d (cuDNN)
+ * (fastflow/layers/conv.py:102-107).  All of those are covered here.
+ *
+ * Conventions
+ *   - fp32, contiguous NCHW device memory.  A tensor is [B, G*C, H, W]: G independent
+ *     groups of C channels.  A reference PaddedConv2d is G = 1; a FastFlowUnit is G = 4
+ *     with orders (TL, TR, BL, BR) on its four channel quarters (fastflow/fastflow.py:24-48).
+ *   - weights are [G*C, C, kH, kW] = the G PaddedConv2d `conv.weight` tensors concatenated
+ *     on dim 0, each in its STORED orientation (already flipped for TR/BL/BR by
+ *     layers/conv.py:72-79).  No host-side flips are ever needed.
+ *   - `orders` packs 2 bits per group, group g at bits [2g, 2g+2):
+ *     bit0 = padded on the right, bit1 = padded at the bottom
+ *     (TL = 0, TR = 1, BL = 2, BR = 3; layers/conv.py:41-55).  G <= 16.
+ *     FINC_ORDERS_UNIT is the FastFlowUnit packing.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream) of the calling thread's current CUDA device, allocates
+ *     nothing, keeps no state between calls, and returns 0 or a negative FINC_E_* code /
+ *     positive cudaError_t.  It never throws.
+ *   - outputs must not alias inputs, except finc_inverse_f32 where x == z is allowed.
+ */
+#ifndef FINCFLOW_B200_H_
+#define FINCFLOW_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FINC_ABI_VERSION 1
+
+#define FINC_ORDER_TL 0u
+#define FINC_ORDER_TR 1u
+#define FINC_ORDER_BL 2u
+#define FINC_ORDER_BR 3u
+#define FINC_ORDERS_UNIT 0xE4u /* TL | TR<<2 | BL<<4 | BR<<6 */
+
+/* flags */
+#define FINC_FLAG_NAIVE 1u        /* force the generic one-thread-per-output kernels (testing) */
+#define FINC_FLAG_NO_MASK 2u      /* backward_weight: do NOT apply the FInC gradient mask */
+#define FINC_FLAG_ACCUMULATE 4u   /* backward_weight: dw += result instead of dw = result */
+
+/* error codes (negative); positive return values are cudaError_t */
+#define FINC_OK 0
+#define FINC_E_BADARG (-1)     /* null pointer, non-positive dimension, G > 16, ... */
+#define FINC_E_WORKSPACE (-2)  /* workspace too small */
+#define FINC_E_UNSUPPORTED (-3)
+
+int finc_abi_version(void);
+const char* finc_error_string(int code);
+
+/* Bind the library's CUDA runtime to `device` for the calling thread (call once after
+ * selecting the device in the host framework, e.g. after torch.cuda.set_device). */
+int finc_set_device(int device);
+/* Number of SMs of the current device (148 on B200); <0 on error. */
+int finc_sm_count(void);
+
+/* z[n, gC+o, h, w] = sum_{i,a,b} w[gC+o, i, a, b] * x[n, gC+i, h+r_g(a), w+c_g(b)]
+ * and, when logdet != NULL, logdet[n] = H*W * sum_g sum_o log|w[gC+o, o, a*_g, b*_g]|
+ * for n < B (the reference returns the python float 0.0 because that diagonal is 1).
+ * Replaces PaddedConv2d.forward (layers/conv.py:102-107: F.pad + cuDNN conv) and
+ * FastFlowUnit.forward (fastflow/fastflow.py:31-50: chunk, 4 pads, 4 convs, cat). */
+int finc_forward_f32(const float* x, const float* w, float* z, float* logdet,
+                     int B, int G, int C, int H, int W, int kH, int kW,
+                     unsigned orders, unsigned flags, void* stream);
+
+/* dx[n, gC+i, p, q] = sum_{o,a,b} w[gC+o, i, a, b] * dz[n, gC+o, p-r_g(a), q-c_g(b)]
+ * Replaces the cuDNN dgrad autograd runs for layers/conv.py:102-105 (plus the
+ * pad/chunk/cat backward slices of fastflow/fastflow.py:31-50). */
+int finc_backward_input_f32(const float* dz, const float* w, float* dx,
+                            int B, int G, int C, int H, int W, int kH, int kW,
+                            unsigned orders, unsigned flags, void* stream);
+
+/* dw[gC+o, i, a, b] = sum_{n,h,w} dz[n, gC+o, h, w] * x[n, gC+i, h+r_g(a), w+c_g(b)]
+ * then (unless FINC_FLAG_NO_MASK) dw[gC+o, i, a*_g, b*_g] = 0 for i >= o.
+ * Replaces cuDNN wgrad + PaddedConv2d.reset_gradients / clear_grad
+ * (layers/conv.py:81-99, train/experiment.py:16-18,250).  `dw` may point into a flat
+ * gradient bucket.  `workspace` must hold finc_backward_weight_workspace_bytes(...)
+ * bytes of device memory (contents irrelevant on entry). */
+size_t finc_backward_weight_workspace_bytes(int B, int G, int C, int H, int W, int kH, int kW);
+int finc_backward_weight_f32(const float* dz, const float* x, float* dw,
+                             void* workspace, size_t workspace_bytes,
+                             int B, int G, int C, int H, int W, int kH, int kW,
+                             unsigned orders, unsigned flags, void* stream);
+
+/* Solve forward(x) = z for x by anti-diagonal wavefront substitution, all groups in one
+ * launch, unit diagonal assumed (no division), `x` need not be zero-filled:
+ *   x[n,o,h,w] = z[n,o,h,w] - sum_{(a,b)!=(a*,b*), i} w[o,i,a,b] x[n,i,h+r(a),w+c(b)]
+ *                           - sum_{i<o} w[o,i,a*,b*] x[n,i,h,w]
+ * Replaces cinc_cuda_level2.inverse / FastFlowUnit.reverse_level2 including its six
+ * flips, three cats and zeros_like (fastflow/fastflow.py:78-100,
+ * utils/fastflow_cuda_inverse/cinc_cuda_kernel_level2.cu:14-136: (H+W-1)*Cq launches each
+ * followed by cudaDeviceSynchronize), cinc_cuda_level1.inverse / PaddedConv2d.reverse_cuda
+ * (cinc_cuda_kernel_level1.cu:14-131, layers/conv.py:191-218) and the Cython CPU solver
+ * behind PaddedConv2d.reverse (layers/conv.py:109-163, solve_parallel_mc.pyx:77-126). */
+int finc_inverse_f32(const float* z, const float* w, float* x,
+                     int B, int G, int C, int H, int W, int kH, int kW,
+                     unsigned orders, unsigned flags, void* stream);
+
+/* dw[gC+o, i, a*_g, b*_g] = 0 for i >= o.  Replaces PaddedConv2d.reset_gradients
+ * (layers/conv.py:98-99: H2D copy of the CPU mask + multiply). */
+int finc_apply_grad_mask_f32(float* dw, int G, int C, int kH, int kW,
+                             unsigned orders, void* stream);
+
+/* logdet[n] = H*W * sum_g sum_o log|w[gC+o, o, a*_g, b*_g]|, n < B.
+ * Replaces PaddedConv2d.logdet (layers/conv.py:220-221, constant 0.0). */
+int finc_logdet_f32(const float* w, float* logdet, int B, int G, int C, int H, int W,
+                    int kH, int kW, unsigned orders, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FINCFLOW_B200_H_ */

@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- FInC hot-path benchmark (driver contract in the task statement).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[2], the config the metric's "1/2/4/8 B200" is quoted on):
+the FInC-unit skeleton of the CIFAR-10-shaped FInCFlow -- 3 levels x 16 FastFlowUnits on
+[256,12,16,16], [256,24,8,8], [256,48,4,4] (k=3), per-GPU batch 256 (weak scaling), fp32,
+synthetic N(0,1) inputs, reference-initialised weights.  One step = one pass of the hot path
+over one batch: forward+logdet (+standard-normal log-prob), backward dX, masked dW into the
+flat gradient bucket, [NCCL all-reduce when N>1], Adam, then one inverse (sampling) pass.
+metric = images/sec of that step (whole job, all GPUs).
+
+  value  inputs resident in HBM; input/activation sets rotate over 3 slots (> L2 in total)
+  e2e    the same step through the public API (HotPathRunner(host_io=True)): every step copies
+         that step's inputs from pinned host memory and reads logp + samples back
+  roofline  dominant kernel family: algorithmic bytes per launch / average launch duration,
+         from CUDA events recorded at the phase boundaries inside the timed region
+  cpu_baseline / --impl reference  the reference's own CPU path (torch CPU conv + autograd +
+         its Cython wavefront solver from oracle/_ref) on the host cores, same step
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+PER_GPU_BATCH = 256
+UNITS_PER_LEVEL = 16
+KSIZE = 3
+WORKLOAD = ("cifar10_finc_stack: FInC-unit skeleton of the CIFAR-10-shaped FInCFlow (BASELINE configs[2]): "
+            "3 levels x 16 FastFlowUnits on [256,12,16,16],[256,24,8,8],[256,48,4,4], k=3; "
+            "step = fwd+logdet+base logp, bwd dX, masked dW, Adam, inverse sampling pass")
+
+
+def levels():
+    from fincflow_b200.stack import cifar10_levels
+
+    return cifar10_levels(UNITS_PER_LEVEL, KSIZE)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampled DURING the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.window = index, [], False, [None, None]
+        self.max_mhz = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz, rs))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        t0, t1 = self.window
+        inside = [s for s in self.samples if t0 is not None and t0 <= s[0] <= t1]
+        use = inside or self.samples[-5:]
+        bits = 0
+        for s in use:
+            bits |= s[2]
+        reasons = sorted({name for bit, name in self.REASONS.items() if bits & bit})
+        return {"sm_mhz": statistics.median(s[1] for s in use), "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(inside)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's CPU path on the host cores
+# ------------------------------------------------------------------------------------------
+def run_reference_cpu(steps, warmup, max_seconds=None):
+    from oracle.reference_path import ReferenceCpuStack, solver_kind
+
+    ref = ReferenceCpuStack(levels(), PER_GPU_BATCH, seed=0)
+    try:
+        for _ in range(warmup):
+            ref.step()
+        times = []
+        t_start = time.perf_counter()
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            ref.step()
+            times.append(time.perf_counter() - t0)
+            if max_seconds is not None and time.perf_counter() - t_start > max_seconds:
+                break
+    finally:
+        ref.close()
+    total = sum(times)
+    return {
+        "value": PER_GPU_BATCH * len(times) / total, "unit": "images/s", "cores": ref.threads,
+        "kind": solver_kind(),
+        "sample": f"{len(times)} full steps of the same workload at batch {PER_GPU_BATCH} "
+                  f"(torch CPU conv/autograd on {ref.threads} threads; inverse = reference Cython solver, "
+                  f"batch sharded over {ref.nshards} forked workers)",
+        "steps": len(times), "ms_per_step": 1e3 * total / len(times),
+    }
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    r = run_reference_cpu(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "images/sec fwd+logdet, train step, and inverse sampling", "value": r["value"],
+        "unit": "images/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "per_gpu_batch": PER_GPU_BATCH, "device": "host CPU"},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def algorithmic_bytes(phase, lv, B):
+    """fp32, per FastFlowUnit on [B,C,H,W]: forward / backward-input / inverse
+    read one tensor and write one (8 B/element); backward-weight reads two (8 B/element,
+    dW itself negligible)."""
+    return 8 * B * lv.channels * lv.height * lv.width
+
+
+def kernel_detail(torch, _native, dev, peak):
+    """each kernel family alone at the three level shapes: batch 256 (the workload) and a
+    batch large enough to stream from HBM; L2 flushed before every timed launch."""
+    from fincflow_b200.fastflow import FastFlowUnit
+
+    flush = torch.empty(160 * 1024 * 1024 // 4, device=dev)
+    out = []
+    for (CT, H, W) in ((12, 16, 16), (24, 8, 8), (48, 4, 4)):
+        for B in (PER_GPU_BATCH, 16384):
+            unit = FastFlowUnit(CT, CT, (KSIZE, KSIZE)).to(dev)
+            w = unit.weight.detach()
+            x = torch.randn(B, CT, H, W, device=dev)
+            dz = torch.randn_like(x)
+            y = torch.empty_like(x)
+            dw = torch.empty_like(w)
+            ws = torch.empty(_native.backward_weight_workspace_bytes(B, 4, CT // 4, H, W, KSIZE, KSIZE),
+                             dtype=torch.uint8, device=dev)
+            fns = {
+                "forward_logdet": lambda: _native.forward(x, w, out=y, want_logdet=False),
+                "backward_input": lambda: _native.backward_input(dz, w, out=y),
+                "backward_weight": lambda: _native.backward_weight(dz, x, (KSIZE, KSIZE), out=dw, workspace=ws),
+                "inverse": lambda: _native.inverse(x, w, out=y),
+            }
+            nbytes = 8 * x.numel()
+            for name, fn in fns.items():
+                for _ in range(3):
+                    fn()
+                ts = []
+                for _ in range(7):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    fn()
+                    e1.record()
+                    e1.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                us = 1e3 * statistics.median(ts)
+                out.append({"kernel": name, "shape": [B, CT, H, W], "us": round(us, 2),
+                            "GBps": round(nbytes / us / 1e3, 1), "frac_of_hbm_peak": round(nbytes / us / 1e3 / peak, 3),
+                            "images_per_s": round(B / us * 1e6)})
+            del x, dz, y
+    return out
+
+
+def main_ours(args):
+    import torch
+
+    from fincflow_b200 import _native
+    from fincflow_b200.stack import FincStack, HotPathRunner
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback in the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    K, Wm = args.steps, max(args.warmup, 3)
+    B = PER_GPU_BATCH
+    lvls = levels()
+    peak, peak_src = measured_peak()
+
+    torch.manual_seed(0)  # same weights on every rank
+    stack = FincStack(lvls).to(dev)
+    NSLOT = 3
+    runner = HotPathRunner(stack, B, dev, slots=NSLOT, process_group=pg)
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)  # different data per rank
+    for s in runner.slots:
+        for li in range(len(lvls)):
+            s.acts[li][0].normal_(generator=g)
+            s.zin[li].normal_(generator=g)
+    runner.prepare()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    nph = len(runner.PHASES)
+    for i in range(Wm):
+        runner.step(i % NSLOT)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(nph + 1)] for _ in range(K)]
+    barrier()
+    sampler.window[0] = time.perf_counter()
+    for i in range(K):
+        runner.step(i % NSLOT, evs[i])
+    barrier()
+    sampler.window[1] = time.perf_counter()
+    elapsed_ms = evs[0][0].elapsed_time(evs[K - 1][nph])
+    phase_ms = [sum(evs[i][p].elapsed_time(evs[i][p + 1]) for i in range(K)) / K for p in range(nph)]
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = B * world * K / (elapsed_ms * 1e-3)
+
+    # ---- e2e: same step through the public API with HOST buffers --------------------------------
+    del runner
+    torch.cuda.empty_cache()
+    ESLOT = 2
+    e2e_runner = HotPathRunner(stack, B, dev, slots=ESLOT, host_io=True, process_group=pg)
+    cpu_gen = torch.Generator().manual_seed(2000 + rank)
+    for s in e2e_runner.slots:
+        for li in range(len(lvls)):
+            s.x_host[li].normal_(generator=cpu_gen)
+            s.z_host[li].normal_(generator=cpu_gen)
+    e2e_runner.prepare()
+    for i in range(Wm):
+        e2e_runner.step(i % ESLOT)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        e2e_runner.step(i % ESLOT)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    logp_last = float(e2e_runner.slots[(K - 1) % ESLOT].logp_host[0].mean())
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = B * world * K / (e2e_ms * 1e-3)
+    act_bytes = sum(4 * B * lv.dim for lv in lvls)
+    h2d = 2 * act_bytes                                  # x and z per level
+    d2h = act_bytes + sum(4 * B for _ in lvls)           # samples + logp
+    launches = e2e_runner.launches_per_step
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+    clocks = sampler.summary()
+
+    # ---- roofline of the dominant kernel family ----------------------------------------------------
+    kernel_phases = {"forward_logdet": ("finc::conv_warp_kernel (forward)", sum(lv.n_units for lv in lvls)),
+                     "backward_input": ("finc::conv_warp_kernel (transposed)", sum(lv.n_units - 1 for lv in lvls)),
+                     "backward_weight": ("finc::wgrad_kernel", sum(lv.n_units for lv in lvls)),
+                     "inverse": ("finc::inverse_warp_kernel", sum(lv.n_units for lv in lvls))}
+    pm = dict(zip(HotPathRunner.PHASES, phase_ms))
+    dom = max(kernel_phases, key=lambda p: pm[p])
+    kname, nlaunch = kernel_phases[dom]
+    if dom == "forward_logdet":
+        nlaunch += len(lvls)  # + one gaussian_logp kernel per level in that phase
+    bytes_phase = sum(algorithmic_bytes(dom, lv, B) * (lv.n_units - (1 if dom == "backward_input" else 0)) for lv in lvls)
+    if dom == "forward_logdet":
+        bytes_phase += sum(8 * B * lv.dim for lv in lvls)  # gaussian_logp: read z, write dz
+    avg_us = 1e3 * pm[dom] / nlaunch
+    achieved = bytes_phase / nlaunch / avg_us / 1e3  # GB/s
+    traffic = None
+    try:
+        with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(dom)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": kname, "phase": dom,
+                "launches_per_step": nlaunch, "avg_launch_us": round(avg_us, 3),
+                "algorithmic_bytes_per_launch": bytes_phase // nlaunch, "peak_source": peak_src,
+                "note": "batch-256 launches move 1.6-6.3 MB each (<1 us at peak): launch/latency-bound; "
+                        "see `kernels` for the same kernels streaming from HBM at batch 16384"}
+
+    line = None
+    if rank == 0:
+        detail = kernel_detail(torch, _native, dev, peak) if (world == 1 and not args.no_detail) else None
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            r = run_reference_cpu(steps=6, warmup=1, max_seconds=25.0)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = {
+            "metric": "images/sec fwd+logdet, train step, and inverse sampling", "value": round(value, 1),
+            "unit": "images/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(elapsed_ms / K, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "units_per_level": UNITS_PER_LEVEL,
+                       "kernel_size": KSIZE, "parallelism": f"dp{world} (batch sharded, NCCL all-reduce of the flat FInC "
+                       "gradient bucket in the train step only; sampling without collective)",
+                       "l2": f"{NSLOT} rotating input/activation sets (~{NSLOT * 0.2:.1f} GB total, > 126 MB L2); "
+                             "intermediates of a step stay L2-resident as in a real flow",
+                       "execution": "one CUDA graph per phase (forward, backward-input, backward-weight, optimizer, inverse)"},
+            "phases_ms": {k: round(v, 4) for k, v in pm.items()},
+            "phase_images_per_s": {
+                "forward_logdet": round(B * world / (pm["forward_logdet"] * 1e-3)),
+                "train_step": round(B * world / ((pm["forward_logdet"] + pm["backward_input"] + pm["backward_weight"]
+                                                  + pm["optimizer"]) * 1e-3)),
+                "inverse_sampling": round(B * world / (pm["inverse"] * 1e-3))},
+            "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(e2e_ms / K, 4), "api": "fincflow_b200.stack.HotPathRunner(host_io=True).step",
+                    "check_mean_logp_level0": logp_last},
+            "gpu_launches": launches * K,
+            "gpu_launches_per_step": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "kernels": detail,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-detail", action="store_true", help="skip the per-kernel detail table")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

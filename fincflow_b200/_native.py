@@ -21,16 +21,19 @@ ORDERS_UNIT = 0xE4  # TL | TR<<2 | BL<<4 | BR<<6   (fastflow/fastflow.py:24-27)
 FLAG_NAIVE = 1
 FLAG_NO_MASK = 2
 FLAG_ACCUMULATE = 4
+FLAG_LOGDET_ACCUMULATE = 8
 
 # every symbol declared in include/fincflow_b200.h
 SYMBOLS = (
     "finc_abi_version", "finc_error_string", "finc_set_device", "finc_sm_count",
     "finc_forward_f32", "finc_backward_input_f32", "finc_backward_weight_workspace_bytes",
     "finc_backward_weight_f32", "finc_inverse_f32", "finc_apply_grad_mask_f32", "finc_logdet_f32",
+    "finc_gaussian_logp_f32",
 )
 
 _lib = None
 _tls = threading.local()
+launch_count = 0  # kernels of ours enqueued through this module (bench.py's gpu_launches)
 
 
 class FincNativeError(RuntimeError):
@@ -62,8 +65,9 @@ def load():
     lib.finc_inverse_f32.argtypes = [p, p, p, *dims, u, u, p]
     lib.finc_apply_grad_mask_f32.argtypes = [p, i, i, i, i, u, p]
     lib.finc_logdet_f32.argtypes = [p, p, *dims, u, p]
+    lib.finc_gaussian_logp_f32.argtypes = [p, p, p, p, ctypes.c_float, i, ctypes.c_long, p]
     for f in ("finc_set_device", "finc_forward_f32", "finc_backward_input_f32", "finc_backward_weight_f32",
-              "finc_inverse_f32", "finc_apply_grad_mask_f32", "finc_logdet_f32"):
+              "finc_inverse_f32", "finc_apply_grad_mask_f32", "finc_logdet_f32", "finc_gaussian_logp_f32"):
         getattr(lib, f).restype = i
     if lib.finc_abi_version() != 1:
         raise FincNativeError("libfincflow_b200.so ABI version mismatch; rebuild")
@@ -78,7 +82,9 @@ def pack_orders(orders) -> int:
     return v
 
 
-def _check(rc: int, what: str):
+def _check(rc: int, what: str, launches: int = 1):
+    global launch_count
+    launch_count += launches
     if rc != 0:
         msg = load().finc_error_string(rc).decode()
         raise FincNativeError(f"{what} failed: {msg} (code {rc})")
@@ -95,7 +101,7 @@ def _prep(t: torch.Tensor, name: str) -> torch.Tensor:
 def _bind_device(t: torch.Tensor):
     dev = t.device.index
     if getattr(_tls, "device", None) != dev:
-        _check(load().finc_set_device(dev), "finc_set_device")
+        _check(load().finc_set_device(dev), "finc_set_device", 0)
         _tls.device = dev
 
 
@@ -113,30 +119,38 @@ def _dims(x: torch.Tensor, w: torch.Tensor, G: int):
     return B, G, C, H, W, int(w.shape[2]), int(w.shape[3])
 
 
-def forward(x, w, G=4, orders=ORDERS_UNIT, want_logdet=True, flags=0):
-    """z, logdet[B] (or None).  C ABI: finc_forward_f32."""
+def forward(x, w, G=4, orders=ORDERS_UNIT, want_logdet=True, flags=0, out=None, logdet_out=None):
+    """z, logdet[B] (or None).  C ABI: finc_forward_f32.  With `logdet_out` and
+    FLAG_LOGDET_ACCUMULATE the layer's logdet is added into a running [B] accumulator."""
     x, w = _prep(x, "x"), _prep(w, "weight")
     d = _dims(x, w, G)
     _bind_device(x)
-    z = torch.empty_like(x)
-    logdet = torch.empty(d[0], dtype=torch.float32, device=x.device) if want_logdet else None
+    z = torch.empty_like(x) if out is None else out
+    if logdet_out is not None:
+        logdet, want_logdet = logdet_out, True
+    else:
+        logdet = torch.empty(d[0], dtype=torch.float32, device=x.device) if want_logdet else None
     _check(load().finc_forward_f32(x.data_ptr(), w.data_ptr(), z.data_ptr(),
                                    logdet.data_ptr() if want_logdet else None,
                                    *d, orders, flags, _stream(x)), "finc_forward_f32")
     return z, logdet
 
 
-def backward_input(dz, w, G=4, orders=ORDERS_UNIT, flags=0):
+def backward_input(dz, w, G=4, orders=ORDERS_UNIT, flags=0, out=None):
     dz, w = _prep(dz, "dz"), _prep(w, "weight")
     d = _dims(dz, w, G)
     _bind_device(dz)
-    dx = torch.empty_like(dz)
+    dx = torch.empty_like(dz) if out is None else out
     _check(load().finc_backward_input_f32(dz.data_ptr(), w.data_ptr(), dx.data_ptr(), *d, orders, flags,
                                           _stream(dz)), "finc_backward_input_f32")
     return dx
 
 
-def backward_weight(dz, x, ksize, G=4, orders=ORDERS_UNIT, flags=0, out=None):
+def backward_weight_workspace_bytes(B, G, C, H, W, kH, kW) -> int:
+    return int(load().finc_backward_weight_workspace_bytes(B, G, C, H, W, kH, kW))
+
+
+def backward_weight(dz, x, ksize, G=4, orders=ORDERS_UNIT, flags=0, out=None, workspace=None):
     """Masked dW [G*C, C, kH, kW] (FLAG_NO_MASK for the raw gradient).  `out` may be a view
     into a flat gradient bucket; FLAG_ACCUMULATE adds into it."""
     dz, x = _prep(dz, "dz"), _prep(x, "x")
@@ -149,8 +163,11 @@ def backward_weight(dz, x, ksize, G=4, orders=ORDERS_UNIT, flags=0, out=None):
     elif not (out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and out.numel() == G * C * C * kH * kW):
         raise FincNativeError("backward_weight: `out` must be a contiguous float32 CUDA tensor of G*C*C*kH*kW elements")
     lib = load()
-    nbytes = lib.finc_backward_weight_workspace_bytes(B, G, C, H, W, kH, kW)
-    ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=x.device)
+    if workspace is None:
+        nbytes = lib.finc_backward_weight_workspace_bytes(B, G, C, H, W, kH, kW)
+        ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=x.device)
+    else:
+        ws = workspace
     _check(lib.finc_backward_weight_f32(dz.data_ptr(), x.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
                                         B, G, C, H, W, kH, kW, orders, flags, _stream(x)),
            "finc_backward_weight_f32")
@@ -186,6 +203,22 @@ def logdet(w, B, H, W, G=4, orders=ORDERS_UNIT):
     _check(load().finc_logdet_f32(w.data_ptr(), out.data_ptr(), B, G, C, H, W, kH, kW, orders, _stream(w)),
            "finc_logdet_f32")
     return out
+
+
+def gaussian_logp(z, logdet=None, dz_scale=None, logp_out=None, dz_out=None):
+    """logp[B] of a standard normal (+ logdet) and optionally dz = dz_scale * z."""
+    z = _prep(z, "z")
+    _bind_device(z)
+    B = int(z.shape[0])
+    D = z.numel() // max(B, 1)
+    logp = torch.empty(B, dtype=torch.float32, device=z.device) if logp_out is None else logp_out
+    dz = None
+    if dz_scale is not None:
+        dz = torch.empty_like(z) if dz_out is None else dz_out
+    _check(load().finc_gaussian_logp_f32(z.data_ptr(), None if logdet is None else logdet.data_ptr(), logp.data_ptr(),
+                                         None if dz is None else dz.data_ptr(), float(dz_scale or 0.0), B, D,
+                                         _stream(z)), "finc_gaussian_logp_f32")
+    return logp, dz
 
 
 def sm_count() -> int:

@@ -83,12 +83,12 @@ int finc_forward_f32(const float* x, const float* w, float* z, float* logdet, in
     cudaStream_t st = (cudaStream_t)stream;
     int rc = 0;
     bool handled = false;
-    if (!(flags & FINC_FLAG_NAIVE)) rc = launch_conv_fast(x, w, z, logdet, s, false, st, &handled);
+    if (!(flags & FINC_FLAG_NAIVE)) rc = launch_conv_fast(x, w, z, logdet, (flags & FINC_FLAG_LOGDET_ACCUMULATE) != 0, s, false, st, &handled);
     if (rc) return rc;
     if (handled) return FINC_OK;  // logdet was written by the fused epilogue
     rc = launch_conv_naive(x, w, z, s, false, st);
     if (rc) return rc;
-    if (logdet) rc = launch_logdet(w, logdet, s, st);
+    if (logdet) rc = launch_logdet(w, logdet, (flags & FINC_FLAG_LOGDET_ACCUMULATE) != 0, s, st);
     return rc;
 }
 
@@ -101,7 +101,7 @@ int finc_backward_input_f32(const float* dz, const float* w, float* dx, int B, i
     cudaStream_t st = (cudaStream_t)stream;
     int rc = 0;
     bool handled = false;
-    if (!(flags & FINC_FLAG_NAIVE)) rc = launch_conv_fast(dz, w, dx, nullptr, s, true, st, &handled);
+    if (!(flags & FINC_FLAG_NAIVE)) rc = launch_conv_fast(dz, w, dx, nullptr, false, s, true, st, &handled);
     if (rc) return rc;
     if (!handled) rc = launch_conv_naive(dz, w, dx, s, true, st);
     return rc;
@@ -155,7 +155,15 @@ int finc_logdet_f32(const float* w, float* logdet, int B, int G, int C, int H, i
     if (!shape_ok(B, G, C, H, W, kH, kW) || !w) return FINC_E_BADARG;
     if (B == 0) return FINC_OK;
     if (!logdet) return FINC_E_BADARG;
-    return launch_logdet(w, logdet, mk(B, G, C, H, W, kH, kW, orders), (cudaStream_t)stream);
+    return launch_logdet(w, logdet, false, mk(B, G, C, H, W, kH, kW, orders), (cudaStream_t)stream);
+}
+
+int finc_gaussian_logp_f32(const float* z, const float* logdet, float* logp, float* dz, float dz_scale, int B,
+                           long D, void* stream) {
+    if (B < 0 || D < 1) return FINC_E_BADARG;
+    if (B == 0) return FINC_OK;
+    if (!z || !logp) return FINC_E_BADARG;
+    return launch_gaussian_logp(z, logdet, logp, dz, dz_scale, B, D, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -93,8 +93,8 @@ int sm_count_cached();
 size_t max_optin_smem_cached();
 
 // launchers implemented by the per-kernel translation units; all return cudaError_t as int
-int launch_conv_fast(const float* x, const float* w, float* y, float* logdet, const Shape& s, bool transpose,
-                     cudaStream_t st, bool* handled);
+int launch_conv_fast(const float* x, const float* w, float* y, float* logdet, bool logdet_acc, const Shape& s,
+                     bool transpose, cudaStream_t st, bool* handled);
 int launch_inverse_fast(const float* z, const float* w, float* x, const Shape& s, cudaStream_t st, bool* handled);
 int launch_wgrad_fast(const float* dz, const float* x, float* dw, float* workspace, size_t ws_floats, const Shape& s,
                       unsigned flags, cudaStream_t st, bool* handled);
@@ -104,6 +104,8 @@ int launch_conv_naive(const float* x, const float* w, float* y, const Shape& s, 
 int launch_inverse_naive(const float* z, const float* w, float* x, const Shape& s, cudaStream_t st);
 int launch_wgrad_naive(const float* dz, const float* x, float* dw, const Shape& s, unsigned flags, cudaStream_t st);
 int launch_mask(float* dw, const Shape& s, cudaStream_t st);
-int launch_logdet(const float* w, float* logdet, const Shape& s, cudaStream_t st);
+int launch_logdet(const float* w, float* logdet, bool accumulate, const Shape& s, cudaStream_t st);
+int launch_gaussian_logp(const float* z, const float* logdet, float* logp, float* dz, float dz_scale, int B, long D,
+                         cudaStream_t st);
 
 }  // namespace finc

@@ -38,6 +38,7 @@ struct ConvArgs {
     const float* w;
     float* y;
     float* logdet;    // nullable; [B], written by CTA (0,0) (forward only)
+    int logdet_acc;   // 1: logdet[n] += value
     Shape s;
     int transpose;
     int T;            // tiles per item
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) conv_warp_kernel(const Conv
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, off);
         ld *= (float)H * (float)W;
-        for (int n = lane; n < s.B; n += 32) a.logdet[n] = ld;
+        for (int n = lane; n < s.B; n += 32) a.logdet[n] = a.logdet_acc ? a.logdet[n] + ld : ld;
     }
 
     const int nstrip = W / WT;
@@ -275,14 +276,14 @@ int pick_ob(int C) {
 
 }  // namespace
 
-int launch_conv_fast(const float* x, const float* w, float* y, float* logdet, const Shape& s, bool transpose,
-                     cudaStream_t st, bool* handled) {
+int launch_conv_fast(const float* x, const float* w, float* y, float* logdet, bool logdet_acc, const Shape& s,
+                     bool transpose, cudaStream_t st, bool* handled) {
     *handled = false;
     if (s.kW != 2 && s.kW != 3 && s.kW != 5) return 0;
     const long tile_floats_l = (long)s.C * s.H * s.W;
     if (tile_floats_l * 4 > 64 * 1024) return 0;
     ConvArgs a{};
-    a.x = x; a.w = w; a.y = y; a.logdet = transpose ? nullptr : logdet; a.s = s; a.transpose = transpose ? 1 : 0;
+    a.x = x; a.w = w; a.y = y; a.logdet = transpose ? nullptr : logdet; a.logdet_acc = logdet_acc ? 1 : 0; a.s = s; a.transpose = transpose ? 1 : 0;
     a.tile_floats = (int)tile_floats_l;
     const int OB = pick_ob(s.C);
     const int OBP = OB <= 2 ? OB : ((OB + 3) / 4) * 4;

@@ -144,7 +144,7 @@ __global__ void mask_kernel(float* dw, Shape s) {
 }
 
 // logdet[n] = H*W*sum log|diag corner tap|; one CTA, fixed-order reduction.
-__global__ void logdet_kernel(const float* __restrict__ w, float* __restrict__ logdet, Shape s) {
+__global__ void logdet_kernel(const float* __restrict__ w, float* __restrict__ logdet, Shape s, bool accumulate) {
     __shared__ float red[32];
     float acc = 0.f;
     for (int e = threadIdx.x; e < s.G * s.C; e += blockDim.x) {
@@ -159,7 +159,39 @@ __global__ void logdet_kernel(const float* __restrict__ w, float* __restrict__ l
     float tot = 0.f;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
     tot *= (float)s.H * (float)s.W;
-    for (int n = threadIdx.x; n < s.B; n += blockDim.x) logdet[n] = tot;
+    for (int n = threadIdx.x; n < s.B; n += blockDim.x) logdet[n] = accumulate ? logdet[n] + tot : tot;
+}
+
+// one CTA per image: logp[n] = -0.5*|z_n|^2 - 0.5*D*log(2pi) + logdet[n]; dz = dz_scale*z.
+// fixed-order reduction (deterministic).  reference: train/losses.py:17-45, flowsequential.py:41-44
+__global__ void gaussian_logp_kernel(const float* __restrict__ z, const float* __restrict__ logdet,
+                                     float* __restrict__ logp, float* __restrict__ dz, float dz_scale, int B, long D) {
+    __shared__ float red[32];
+    for (int n = blockIdx.x; n < B; n += gridDim.x) {
+        const float* zn = z + (long)n * D;
+        float acc = 0.f;
+        for (long d = threadIdx.x; d < D; d += blockDim.x) {
+            const float v = zn[d];
+            acc = fmaf(v, v, acc);
+            if (dz) dz[(long)n * D + d] = dz_scale * v;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float tot = 0.f;
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+            logp[n] = -0.5f * tot - 0.5f * (float)D * 1.8378770664093453f + (logdet ? logdet[n] : 0.f);
+        }
+        __syncthreads();
+    }
+}
+
+int launch_gaussian_logp(const float* z, const float* logdet, float* logp, float* dz, float dz_scale, int B, long D,
+                         cudaStream_t st) {
+    gaussian_logp_kernel<<<B < 148 * 8 ? B : 148 * 8, 256, 0, st>>>(z, logdet, logp, dz, dz_scale, B, D);
+    return (int)cudaGetLastError();
 }
 
 int launch_conv_naive(const float* x, const float* w, float* y, const Shape& s, bool transpose, cudaStream_t st) {
@@ -190,8 +222,8 @@ int launch_mask(float* dw, const Shape& s, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
-int launch_logdet(const float* w, float* logdet, const Shape& s, cudaStream_t st) {
-    logdet_kernel<<<1, 256, 0, st>>>(w, logdet, s);
+int launch_logdet(const float* w, float* logdet, bool accumulate, const Shape& s, cudaStream_t st) {
+    logdet_kernel<<<1, 256, 0, st>>>(w, logdet, s, accumulate);
     return (int)cudaGetLastError();
 }
 

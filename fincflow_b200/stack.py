@@ -1,0 +1,267 @@
+"""FincStack: a flow made of FastFlowUnits only (per level a chain of units + standard-normal
+base), and HotPathRunner: its train step / sampling pass as CUDA graphs.
+
+This is the reference's FlowSequential (fastflow/layers/flowsequential.py:21-44,89-115:
+iterate layers, `logdet += layer_logdet`, `base.log_prob(z) + logdet`, reverse = iterate
+reversed) restricted to the hot-path layer, i.e. the FInC-unit skeleton of the multi-scale
+FastFlow models (fastflow/fastflow_cifar_multi_gpu.py:295-313: per level `block_size`
+FastFlowSteps on [B, 4Cq, H, W]).  The Glow glue between the units (ActNorm, Conv1x1,
+Coupling) is out of scope of the hot path.
+
+B200-first choices:
+  * all unit weights live in ONE flat parameter and all masked weight gradients in ONE flat
+    bucket, written directly by the wgrad kernel -- the bucket is what NCCL all-reduces;
+  * per-layer logdet is accumulated by the forward kernel's epilogue into one [B] vector;
+  * a train step / sampling pass is a fixed launch sequence -> captured once per input slot
+    in CUDA graphs (launch-bound: ~1 us of HBM traffic per unit at batch 256).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+import torch.nn as nn
+
+from . import _native
+from .layers.conv import ORDERS, init_finc_weight_
+from .ops import finc_conv, finc_inverse
+
+
+@dataclass(frozen=True)
+class LevelSpec:
+    channels: int   # 4*Cq
+    height: int
+    width: int
+    n_units: int
+    kernel_size: tuple = (3, 3)
+
+    @property
+    def cq(self):
+        return self.channels // 4
+
+    @property
+    def unit_numel(self):
+        return 4 * self.cq * self.cq * self.kernel_size[0] * self.kernel_size[1]
+
+    @property
+    def dim(self):
+        return self.channels * self.height * self.width
+
+
+# FInC-unit skeletons of the reference's model scripts (SURVEY.md section 8 shape table)
+def cifar10_levels(n_units=16, k=3):
+    """fastflow_cifar_multi_gpu.py:295-313 with n_blocks=3, block_size=16"""
+    return [LevelSpec(12, 16, 16, n_units, (k, k)), LevelSpec(24, 8, 8, n_units, (k, k)),
+            LevelSpec(48, 4, 4, n_units, (k, k))]
+
+
+def mnist_levels(n_units=16, k=3):
+    """fastflow_mnist_multi_gpu.py:299-314,414-416: n_blocks=2, block_size=16, ONE final step"""
+    return [LevelSpec(4, 14, 14, n_units, (k, k)), LevelSpec(8, 7, 7, 1, (k, k))]
+
+
+def imagenet32_levels(n_units=48, k=3):
+    return cifar10_levels(n_units, k)
+
+
+def imagenet64_levels(n_units=48, k=3):
+    """fastflow_imagenet64_multi_gpu.py:299-314,424-426: 4 blocks x 48, ONE final step"""
+    return [LevelSpec(12, 32, 32, n_units, (k, k)), LevelSpec(24, 16, 16, n_units, (k, k)),
+            LevelSpec(48, 8, 8, n_units, (k, k)), LevelSpec(96, 4, 4, 1, (k, k))]
+
+
+class FincStack(nn.Module):
+    def __init__(self, levels):
+        super().__init__()
+        self.levels = list(levels)
+        self.offsets = []
+        off = 0
+        for lv in self.levels:
+            assert lv.channels % 4 == 0
+            self.offsets.append([off + u * lv.unit_numel for u in range(lv.n_units)])
+            off += lv.n_units * lv.unit_numel
+        self.flat = nn.Parameter(torch.empty(off))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for li, lv in enumerate(self.levels):
+            for u in range(lv.n_units):
+                w = self.unit_weight(li, u).data
+                for q, order in enumerate(ORDERS):
+                    init_finc_weight_(w[q * lv.cq:(q + 1) * lv.cq], order)
+
+    def unit_weight(self, li, u, flat=None):
+        lv = self.levels[li]
+        flat = self.flat if flat is None else flat
+        o = self.offsets[li][u]
+        return flat[o:o + lv.unit_numel].view(4 * lv.cq, lv.cq, *lv.kernel_size)
+
+    # ---- autograd API (FlowSequential semantics, one level) --------------------------------
+    def forward(self, x, level=0):
+        """(z, logp[B]) = units of `level` applied in order, standard-normal base + logdet."""
+        lv = self.levels[level]
+        logdet = None
+        for u in range(lv.n_units):
+            x, ld = finc_conv(x, self.unit_weight(level, u), 4, _native.ORDERS_UNIT, True, True)
+            logdet = ld if logdet is None else logdet + ld
+        logp = -0.5 * x.flatten(1).pow(2).sum(1) - 0.5 * lv.dim * math.log(2 * math.pi) + logdet
+        return x, logp
+
+    def reverse(self, z, level=0):
+        lv = self.levels[level]
+        for u in reversed(range(lv.n_units)):
+            z = finc_inverse(z, self.unit_weight(level, u))
+        return z
+
+
+class _Slot:
+    """static device buffers of one input slot (graphs replay on fixed addresses)"""
+
+    def __init__(self, stack, B, device, pinned):
+        f = dict(dtype=torch.float32, device=device)
+        self.acts, self.logdet, self.logp, self.dzs, self.samp, self.zin = [], [], [], [], [], []
+        self.x_host, self.z_host, self.logp_host, self.samp_host = [], [], [], []
+        for lv in stack.levels:
+            shp = (B, lv.channels, lv.height, lv.width)
+            self.acts.append([torch.empty(shp, **f) for _ in range(lv.n_units + 1)])
+            self.logdet.append(torch.empty(B, **f))
+            self.logp.append(torch.empty(B, **f))
+            self.dzs.append([torch.empty(shp, **f) for _ in range(lv.n_units + 1)])  # dzs[u] = dL/d acts[u]
+            self.zin.append(torch.empty(shp, **f))
+            self.samp.append([torch.empty(shp, **f) for _ in range(2)])
+            if pinned:
+                self.x_host.append(torch.empty(shp, dtype=torch.float32).pin_memory())
+                self.z_host.append(torch.empty(shp, dtype=torch.float32).pin_memory())
+                self.logp_host.append(torch.empty(B, dtype=torch.float32).pin_memory())
+                self.samp_host.append(torch.empty(shp, dtype=torch.float32).pin_memory())
+
+
+class HotPathRunner:
+    """Train step (forward+logdet, base log-prob, backward dX + masked dW into the flat
+    bucket, [all-reduce], Adam) and sampling pass (wavefront inverse chain) of a FincStack.
+
+    The step order is the reference's Experiment.train_epoch (train/experiment.py:226-251):
+    forward -> loss = -mean(logp) -> backward -> FInC gradient mask (here: inside the wgrad
+    kernel) -> optimizer step; sampling is model.sample (train/experiment.py:327-337).
+    """
+
+    PHASES = ("forward_logdet", "backward_input", "backward_weight", "optimizer", "inverse")
+
+    def __init__(self, stack: FincStack, batch: int, device, slots=1, lr=1e-3, host_io=False,
+                 process_group=None, use_graphs=True):
+        self.stack, self.B, self.device = stack, batch, torch.device(device)
+        self.pg = process_group
+        self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)
+        self.host_io, self.use_graphs = host_io, use_graphs
+        self.grad = torch.zeros_like(stack.flat.data)
+        stack.flat.grad = self.grad
+        self.opt = torch.optim.Adam([stack.flat], lr=lr, capturable=True, foreach=False, fused=True)
+        ws = 16
+        for lv in stack.levels:
+            ws = max(ws, _native.backward_weight_workspace_bytes(batch, 4, lv.cq, lv.height, lv.width,
+                                                                 *lv.kernel_size))
+        self.workspace = torch.empty(ws, dtype=torch.uint8, device=self.device)
+        self.slots = [_Slot(stack, batch, self.device, host_io) for _ in range(slots)]
+        self.graphs = [None] * slots
+        self.launches_per_step = None
+        self.copy_stream = torch.cuda.Stream(self.device) if host_io else None
+
+    # ---- the four phases as plain launch sequences on the current stream ----------------------
+    def _forward(self, s):
+        st = self.stack
+        for li, lv in enumerate(st.levels):
+            if self.host_io:
+                s.acts[li][0].copy_(s.x_host[li], non_blocking=True)
+            for u in range(lv.n_units):
+                flags = _native.FLAG_LOGDET_ACCUMULATE if u else 0
+                _native.forward(s.acts[li][u], st.unit_weight(li, u).detach(), flags=flags,
+                                out=s.acts[li][u + 1], logdet_out=s.logdet[li])
+            # logp and dz = d(-mean_n logp)/dz = z / (B * world)
+            _native.gaussian_logp(s.acts[li][lv.n_units], s.logdet[li], 1.0 / (self.B * self.world),
+                                  logp_out=s.logp[li], dz_out=s.dzs[li][lv.n_units])
+            if self.host_io:
+                s.logp_host[li].copy_(s.logp[li], non_blocking=True)
+
+    def _backward_input(self, s):
+        """dzs[u] = dL/d acts[u] for u = n-1 .. 1 (the data gradient of unit 0 is never needed)"""
+        st = self.stack
+        for li, lv in enumerate(st.levels):
+            for u in reversed(range(1, lv.n_units)):
+                _native.backward_input(s.dzs[li][u + 1], st.unit_weight(li, u).detach(), out=s.dzs[li][u])
+
+    def _backward_weight(self, s):
+        """masked dW of every unit, written straight into the flat gradient bucket"""
+        st = self.stack
+        for li, lv in enumerate(st.levels):
+            for u in range(lv.n_units):
+                _native.backward_weight(s.dzs[li][u + 1], s.acts[li][u], lv.kernel_size,
+                                        out=st.unit_weight(li, u, self.grad), workspace=self.workspace)
+
+    def _optimizer(self, s):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grad, group=self.pg)  # NCCL over NVLink, training only
+        self.opt.step()
+
+    def _inverse(self, s):
+        st = self.stack
+        for li, lv in enumerate(st.levels):
+            if self.host_io:
+                s.zin[li].copy_(s.z_host[li], non_blocking=True)
+            src, cur = s.zin[li], 0
+            for u in reversed(range(lv.n_units)):
+                _native.inverse(src, st.unit_weight(li, u).detach(), out=s.samp[li][cur])
+                src, cur = s.samp[li][cur], cur ^ 1
+            if self.host_io:
+                s.samp_host[li].copy_(src, non_blocking=True)
+            s.sample_out = getattr(s, "sample_out", {})
+            s.sample_out[li] = src
+
+    def _phase_fns(self):
+        return (self._forward, self._backward_input, self._backward_weight, self._optimizer, self._inverse)
+
+    # ---- graphs -------------------------------------------------------------------------------
+    def prepare(self):
+        """warm up eagerly (binds the device, sets kernel attributes, initialises Adam state),
+        then capture one CUDA graph per (slot, phase).  The all-reduce stays outside graphs."""
+        for s in self.slots:
+            for fn in self._phase_fns():
+                fn(s)
+        torch.cuda.synchronize(self.device)
+        c0 = _native.launch_count
+        for fn in self._phase_fns():
+            fn(self.slots[0])
+        self.launches_per_step = _native.launch_count - c0
+        torch.cuda.synchronize(self.device)
+        if not self.use_graphs:
+            return
+        for i, s in enumerate(self.slots):
+            gs = []
+            for name, fn in zip(self.PHASES, self._phase_fns()):
+                if name == "optimizer" and self.world > 1:
+                    gs.append(None)  # eager: NCCL all-reduce + Adam
+                    continue
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fn(s)
+                gs.append(g)
+            self.graphs[i] = gs
+        torch.cuda.synchronize(self.device)
+
+    def run_phase(self, slot, phase_idx):
+        s = self.slots[slot]
+        g = self.graphs[slot][phase_idx] if self.graphs[slot] is not None else None
+        if g is not None:
+            g.replay()
+        else:
+            self._phase_fns()[phase_idx](s)
+
+    def step(self, slot=0, events=None):
+        """one full hot-path pass; `events` (len(PHASES)+1 torch.cuda.Event) get phase boundaries"""
+        n = len(self.PHASES)
+        for p in range(n):
+            if events is not None:
+                events[p].record()
+            self.run_phase(slot, p)
+        if events is not None:
+            events[n].record()

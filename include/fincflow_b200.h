@@ -48,6 +48,7 @@ extern "C" {
 #define FINC_FLAG_NAIVE 1u        /* force the generic one-thread-per-output kernels (testing) */
 #define FINC_FLAG_NO_MASK 2u      /* backward_weight: do NOT apply the FInC gradient mask */
 #define FINC_FLAG_ACCUMULATE 4u   /* backward_weight: dw += result instead of dw = result */
+#define FINC_FLAG_LOGDET_ACCUMULATE 8u /* forward: logdet[n] += ... (FlowSequential's `logdet += layer_logdet`) */
 
 /* error codes (negative); positive return values are cudaError_t */
 #define FINC_OK 0
@@ -115,6 +116,15 @@ int finc_apply_grad_mask_f32(float* dw, int G, int C, int kH, int kW,
  * Replaces PaddedConv2d.logdet (layers/conv.py:220-221, constant 0.0). */
 int finc_logdet_f32(const float* w, float* logdet, int B, int G, int C, int H, int W,
                     int kH, int kW, unsigned orders, void* stream);
+
+/* Standard-normal base distribution of a flow that ends in FInC layers:
+ *   logp[n]  = -0.5*sum_d z[n,d]^2 - 0.5*D*log(2*pi) + (logdet ? logdet[n] : 0)
+ *   dz[n,d]  = dz_scale * z[n,d]            (when dz != NULL; d(-mean logp)/dz with dz_scale = 1/B)
+ * Replaces NegativeGaussianLoss.log_prob (train/losses.py:17-45: MultivariateNormal with a dense
+ * D x D identity on cuda:0) + `logprob + logdet` (layers/flowsequential.py:41-44) and the autograd
+ * backward of that sum.  z is [B, D] contiguous. */
+int finc_gaussian_logp_f32(const float* z, const float* logdet, float* logp, float* dz, float dz_scale,
+                           int B, long D, void* stream);
 
 #ifdef __cplusplus
 }

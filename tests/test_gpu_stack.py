@@ -1,0 +1,130 @@
+"""GPU tests of the FInC stack runner (train step + sampling as CUDA graphs) against the
+autograd path and the CPU oracle / reference-path twin."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import finc_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+
+def _small_levels():
+    from fincflow_b200.stack import LevelSpec
+
+    return [LevelSpec(12, 8, 8, 3, (3, 3)), LevelSpec(24, 4, 4, 2, (3, 3)), LevelSpec(8, 7, 7, 1, (3, 3))]
+
+
+@pytest.mark.parametrize("use_graphs", [False, True])
+def test_runner_matches_autograd_and_oracle(use_graphs):
+    from fincflow_b200.stack import FincStack, HotPathRunner
+
+    torch.manual_seed(0)
+    B = 10
+    lv = _small_levels()
+    stack = FincStack(lv).cuda()
+    w0 = stack.flat.detach().clone()
+    runner = HotPathRunner(stack, B, "cuda", slots=2, lr=0.0, use_graphs=use_graphs)  # lr 0: weights stay fixed
+    for s in runner.slots:
+        for li in range(len(lv)):
+            s.acts[li][0].normal_()
+            s.zin[li].normal_()
+    runner.prepare()
+    runner.step(1)
+    torch.cuda.synchronize()
+    assert torch.equal(stack.flat.detach(), w0)
+    s = runner.slots[1]
+    # autograd twin
+    ref = FincStack(lv).cuda()
+    ref.flat.data.copy_(w0)
+    loss = 0
+    for li in range(len(lv)):
+        z, logp = ref(s.acts[li][0], level=li)
+        assert rel_err(s.logp[li].cpu().numpy(), logp.detach().cpu().numpy()) <= 1e-5
+        loss = loss - logp.sum() / B
+        assert torch.equal(z.detach(), s.acts[li][lv[li].n_units])
+        # oracle: logp of the chain
+        h = s.acts[li][0].cpu().numpy()
+        for u in range(lv[li].n_units):
+            h = fo.forward(h, ref.unit_weight(li, u).detach().cpu().numpy())
+        want = -0.5 * (h.reshape(B, -1) ** 2).sum(1) - 0.5 * lv[li].dim * math.log(2 * math.pi)
+        assert rel_err(s.logp[li].cpu().numpy(), want) <= 1e-5
+    loss.backward()
+    assert rel_err(runner.grad.cpu().numpy(), ref.flat.grad.cpu().numpy()) <= 1e-5
+    # masked entries of the bucket are exactly zero
+    g0 = stack.unit_weight(0, 0, runner.grad).cpu().numpy()
+    assert np.array_equal(g0 == 0, fo.apply_grad_mask(np.ones_like(g0)) == 0)
+    # sampling pass == reverse chain == oracle inverse chain
+    for li in range(len(lv)):
+        x = ref.reverse(s.zin[li], level=li)
+        assert torch.equal(x, s.sample_out[li])
+        h = s.zin[li].cpu().numpy()
+        for u in reversed(range(lv[li].n_units)):
+            h = fo.inverse(h, ref.unit_weight(li, u).detach().cpu().numpy())
+        assert rel_err(x.cpu().numpy(), h) <= 1e-5
+
+
+def test_host_io_step_and_adam_update():
+    from fincflow_b200.stack import FincStack, HotPathRunner
+
+    torch.manual_seed(1)
+    B = 6
+    lv = _small_levels()
+    stack = FincStack(lv).cuda()
+    w0 = stack.flat.detach().clone()
+    runner = HotPathRunner(stack, B, "cuda", slots=1, lr=1e-3, host_io=True)
+    s = runner.slots[0]
+    for li in range(len(lv)):
+        s.x_host[li].normal_()
+        s.z_host[li].normal_()
+    runner.prepare()
+    w1 = stack.flat.detach().clone()
+    runner.step(0)
+    torch.cuda.synchronize()
+    w2 = stack.flat.detach()
+    assert not torch.equal(w1, w2)
+    # the FInC invariant survives Adam because masked gradients are exactly zero
+    for li in range(len(lv)):
+        for u in range(lv[li].n_units):
+            a, b = stack.unit_weight(li, u, w0).cpu().numpy(), stack.unit_weight(li, u).detach().cpu().numpy()
+            frozen = fo.apply_grad_mask(np.ones_like(a)) == 0
+            assert np.array_equal(a[frozen], b[frozen])
+    # host results: logp finite, samples invert to the host z through the UPDATED weights
+    for li in range(len(lv)):
+        assert torch.isfinite(s.logp_host[li]).all()
+        h = s.samp_host[li].cuda()
+        for u in range(lv[li].n_units):
+            h, _ = __import__("fincflow_b200")._native.forward(h, stack.unit_weight(li, u).detach(), want_logdet=False)
+        assert (h.cpu() - s.z_host[li]).abs().max().item() <= 1e-4
+
+
+def test_reference_cpu_path_twin_agrees():
+    """bench.py's reference arm computes the same step as the GPU runner"""
+    from fincflow_b200.stack import FincStack, HotPathRunner, LevelSpec
+    from oracle.reference_path import ReferenceCpuStack
+
+    lv = [LevelSpec(12, 8, 8, 2, (3, 3)), LevelSpec(24, 4, 4, 2, (3, 3))]
+    B = 4
+    ref = ReferenceCpuStack(lv, B, seed=5, lr=0.0, threads=1)
+    stack = FincStack(lv).cuda()
+    with torch.no_grad():
+        for li in range(len(lv)):
+            for u in range(lv[li].n_units):
+                stack.unit_weight(li, u).copy_(ref.weights[li][u].detach())
+    runner = HotPathRunner(stack, B, "cuda", slots=1, lr=0.0, use_graphs=False)
+    s = runner.slots[0]
+    for li in range(len(lv)):
+        s.acts[li][0].copy_(ref.x[li])
+        s.zin[li].copy_(ref.z[li])
+    runner.prepare()
+    logps, samples = ref.step()
+    torch.cuda.synchronize()
+    for li in range(len(lv)):
+        assert rel_err(s.logp[li].cpu().numpy(), logps[li].detach().numpy()) <= 1e-5
+        assert rel_err(s.sample_out[li].cpu().numpy(), samples[li].numpy()) <= 1e-5
+        for u in range(lv[li].n_units):
+            assert rel_err(stack.unit_weight(li, u, runner.grad).cpu().numpy(),
+                           ref.weights[li][u].grad.numpy()) <= 1e-5

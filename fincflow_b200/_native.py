@@ -22,6 +22,7 @@ FLAG_NAIVE = 1
 FLAG_NO_MASK = 2
 FLAG_ACCUMULATE = 4
 FLAG_LOGDET_ACCUMULATE = 8
+FLAG_GENERIC_TILED = 16
 
 # every symbol declared in include/fincflow_b200.h
 SYMBOLS = (

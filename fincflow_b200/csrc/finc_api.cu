@@ -139,7 +139,11 @@ int finc_inverse_f32(const float* z, const float* w, float* x, int B, int G, int
     cudaStream_t st = (cudaStream_t)stream;
     int rc = 0;
     bool handled = false;
-    if (!(flags & FINC_FLAG_NAIVE)) rc = launch_inverse_fast(z, w, x, s, st, &handled);
+    if (!(flags & FINC_FLAG_NAIVE)) {
+        if (!(flags & FINC_FLAG_GENERIC_TILED)) rc = launch_inverse_wave(z, w, x, s, st, &handled);
+        if (rc) return rc;
+        if (!handled) rc = launch_inverse_fast(z, w, x, s, st, &handled);
+    }
     if (rc) return rc;
     if (!handled) rc = launch_inverse_naive(z, w, x, s, st);
     return rc;

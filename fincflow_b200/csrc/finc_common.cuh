@@ -96,6 +96,7 @@ size_t max_optin_smem_cached();
 int launch_conv_fast(const float* x, const float* w, float* y, float* logdet, bool logdet_acc, const Shape& s,
                      bool transpose, cudaStream_t st, bool* handled);
 int launch_inverse_fast(const float* z, const float* w, float* x, const Shape& s, cudaStream_t st, bool* handled);
+int launch_inverse_wave(const float* z, const float* w, float* x, const Shape& s, cudaStream_t st, bool* handled);
 int launch_wgrad_fast(const float* dz, const float* x, float* dw, float* workspace, size_t ws_floats, const Shape& s,
                       unsigned flags, cudaStream_t st, bool* handled);
 size_t wgrad_workspace_floats(const Shape& s);

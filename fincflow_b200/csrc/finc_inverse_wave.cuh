@@ -1,0 +1,315 @@
+// finc_inverse_wave.cuh -- specialised wavefront inverse for the shapes FInC flows use
+// (C in {1,2,3,4,6,12,24}, 3x3 / 5x5 kernels).  Same contract and pipeline as
+// finc_inverse.cu (warp-persistent workers, TMA bulk load -> in-place solve in shared
+// memory -> TMA bulk store) with a lower-latency, higher-throughput inner loop:
+//
+//   * lane = (column j, part p), P = 2^k parts per pixel.  The (kH*kW-1) non-corner taps of
+//     a pixel are split over its P lanes (split-K over taps); each lane accumulates the
+//     contribution of its taps to ALL C output channels, then the P partial sums are
+//     combined with log2(P) xor-shuffles.  A 4x4x12 tile therefore keeps 32 lanes busy
+//     (4 columns x 8 parts) instead of 4, a 16x16x3 tile 32 instead of 16.
+//   * the channel-triangular corner solve runs in registers, redundantly on the P lanes of
+//     the pixel (no divergence); lane p writes the channels o == p (mod P).
+//   * weights of the lane's taps and the corner tap live in REGISTERS when they fit
+//     (C <= 6), loaded once per item; otherwise they are vector loads from the
+//     sweep-ordered table in shared memory.
+//   * an item is a STACK of T tiles (n..n+T-1, g) of one group swept as one tall image:
+//     lane j solves stacked row (step - j), so the wavefront never drains between tiles
+//     (a lone 16x16 tile keeps only 52% of the lane-steps busy, a stack of 4 keeps 81%).
+//     Dependencies are cut at tile boundaries exactly like the zero padding does.
+//   * kernel size and channel count are template parameters: tap offsets, bounds and the
+//     triangular solve are fully unrolled; no integer division in the step loop.
+#pragma once
+#include "finc_common.cuh"
+
+namespace finc {
+namespace wave {
+
+constexpr int kMaxWarps = 16;
+
+struct WaveArgs {
+    const float* z;
+    const float* w;
+    float* x;
+    Shape s;
+    int T;  // stacked tiles per item
+    int S;  // pipeline stages per warp
+    int gsplit;
+    int bulk;
+    int tile_floats;
+    int tile_stride;
+    int wk_floats;
+    long n_items;
+};
+
+template <int C>
+struct Pad4 {
+    static constexpr int value = C <= 2 ? C : ((C + 3) / 4) * 4;
+    // floats between consecutive taps of the weight table: an odd number of 16-byte groups, so
+    // the P lanes of a pixel (different taps, same row) hit disjoint banks with LDS.128
+    static constexpr int tap_stride = (C <= 2) ? C * value : (((C * value / 4) % 2 == 1) ? C * value : C * value + 4);
+};
+
+__device__ __forceinline__ void bulk_wait_read_1w() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+template <int C, int KH, int KW, int P>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const WaveArgs a) {
+    constexpr int CPP = Pad4<C>::value;
+    constexpr int TS = Pad4<C>::tap_stride;
+    constexpr int NT = KH * KW - 1;          // non-corner taps
+    constexpr int NTL = (NT + P - 1) / P;    // taps per lane
+    constexpr bool WREG = (NTL * C * C <= 72);  // tap weights in registers
+    constexpr bool CREG = (C <= 6);             // corner weights in registers
+    constexpr int CB = 32 / P;                  // columns per block
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* wk = reinterpret_cast<float*>(smem_raw);
+    const int nwarps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const Shape& s = a.s;
+    const int H = s.H, W = s.W;
+    const int HW = H * W;
+    const int stage_floats = a.T * a.tile_stride;
+    const int wk_pad = (a.wk_floats + 31) & ~31;
+    float* bufs = wk + wk_pad + (size_t)warp * a.S * stage_floats;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wk + wk_pad + (size_t)nwarps * a.S * stage_floats) + warp * a.S;
+
+    const int g_fixed = a.gsplit ? (int)blockIdx.y : -1;
+    const long gw = (long)warp * gridDim.x + blockIdx.x;
+    const long gstride = (long)gridDim.x * nwarps;
+
+    auto item_g = [&](long item) -> int { return a.gsplit ? g_fixed : (int)(item % s.G); };
+    auto item_n0 = [&](long item) -> int { return (int)(a.gsplit ? item : item / s.G) * a.T; };
+    auto issue_load = [&](long item, int st) {  // lane 0 only
+        const int g = item_g(item), n0 = item_n0(item);
+        const int nt = min(a.T, s.B - n0);
+        mbar_arrive_expect_tx(&bars[st], (uint32_t)(nt * a.tile_floats * 4));
+        for (int t = 0; t < nt; ++t)
+            bulk_g2s(bufs + st * stage_floats + t * a.tile_stride, a.z + ((long)(n0 + t) * s.G + g) * a.tile_floats,
+                     (uint32_t)(a.tile_floats * 4), &bars[st]);
+    };
+
+    const int n_pre = a.S == 3 ? 2 : a.S;
+    if (a.bulk && lane == 0) {
+        for (int st = 0; st < a.S; ++st) mbar_init(&bars[st], 1);
+        fence_mbar_init();
+        for (int st = 0; st < n_pre; ++st) {
+            const long item = gw + st * gstride;
+            if (item < a.n_items) issue_load(item, st);
+        }
+    }
+    {
+        // sweep-ordered weights: wk[gl][kh][kw][i][CPP] = Ws[g][o][i][a(kh)][b(kw)]
+        // (padding lanes o >= C of a row are never read into a stored result)
+        constexpr int per_g = C * C * KH * KW;
+        const int ng = a.gsplit ? 1 : s.G;
+        for (int e = threadIdx.x; e < ng * per_g; e += blockDim.x) {
+            const int gl = e / per_g;
+            const int g = a.gsplit ? g_fixed : gl;
+            int r = e - gl * per_g;
+            const int b = r % KW;
+            r /= KW;
+            const int aa = r % KH;
+            r /= KH;
+            const int i = r % C, o = r / C;
+            const int ord = order_of(s.orders, g);
+            const int kh = (ord & 2) ? aa : KH - 1 - aa;
+            const int kw = (ord & 1) ? b : KW - 1 - b;
+            wk[((gl * KH + kh) * KW + kw) * TS + i * CPP + o] = __ldg(a.w + (long)g * per_g + (e - gl * per_g));
+        }
+        __syncthreads();
+    }
+
+    const int jj = lane / P;       // column slot
+    const int p = lane - jj * P;   // part
+    const int ncb = (W + CB - 1) / CB;
+
+    // taps owned by this lane (sweep coordinates); q enumerates (kh,kw) != (0,0) row-major
+    int tkh[NTL], tkw[NTL];
+#pragma unroll
+    for (int m = 0; m < NTL; ++m) {
+        const int q = m * P + p;
+        tkh[m] = (q < NT) ? (q + 1) / KW : KH + H;  // invalid taps never pass the bounds test
+        tkw[m] = (q < NT) ? (q + 1) % KW : 0;
+    }
+
+    long k = 0;
+    for (long item = gw; item < a.n_items; item += gstride, ++k) {
+        const int st = (int)(k % a.S);
+        const int g = item_g(item), n0 = item_n0(item);
+        const int nt = min(a.T, s.B - n0);
+        float* buf = bufs + st * stage_floats;
+        if (a.bulk) {
+            mbar_wait(&bars[st], (uint32_t)((k / a.S) & 1));
+        } else {
+            for (int t = 0; t < nt; ++t) {
+                const float* src = a.z + ((long)(n0 + t) * s.G + g) * a.tile_floats;
+                for (int e = lane; e < a.tile_floats; e += 32) buf[t * a.tile_stride + e] = src[e];
+            }
+            __syncwarp();
+        }
+        const int ord = order_of(s.orders, g);
+        const bool bot = ord & 2, right = ord & 1;
+        const float* wg = wk + (size_t)(a.gsplit ? 0 : g) * KH * KW * TS;
+
+        // per-item register weights
+        float wr[WREG ? NTL : 1][WREG ? C : 1][WREG ? C : 1];
+        float wc[CREG ? C : 1][CREG ? C : 1];
+        int toff[NTL];
+        const float* wp[NTL];
+#pragma unroll
+        for (int m = 0; m < NTL; ++m) {
+            toff[m] = (bot ? tkh[m] : -tkh[m]) * W + (right ? tkw[m] : -tkw[m]);
+            const int q = m * P + p;
+            wp[m] = wg + (size_t)((q < NT ? tkh[m] : 0) * KW + tkw[m]) * TS;
+            if constexpr (WREG) {
+#pragma unroll
+                for (int i = 0; i < C; ++i)
+#pragma unroll
+                    for (int o = 0; o < C; ++o) wr[m][i][o] = (q < NT) ? wp[m][i * CPP + o] : 0.f;
+            }
+        }
+        if constexpr (CREG) {
+#pragma unroll
+            for (int i = 0; i < C; ++i)
+#pragma unroll
+                for (int o = 0; o < C; ++o) wc[i][o] = wg[i * CPP + o];
+        }
+
+        const int R = nt * H;  // stacked rows
+        for (int cb = 0; cb < ncb; ++cb) {
+            const int ws = cb * CB + jj;  // sweep column
+            const int nc = min(CB, W - cb * CB);
+            const bool col_on = jj < nc;
+            const int wst = right ? W - 1 - ws : ws;
+            const int nsteps = R + nc - 1;
+            int hs = -jj;  // sweep row inside the current tile (valid once r >= 0)
+            int r = -jj;   // stacked row
+            float* xt = buf;
+            for (int step = 0; step < nsteps; ++step) {
+                const bool act = col_on && r >= 0 && r < R;
+                float acc[C];
+#pragma unroll
+                for (int o = 0; o < C; ++o) acc[o] = 0.f;
+                int pix = 0;
+                if (act) {
+                    const int h = bot ? H - 1 - hs : hs;
+                    pix = h * W + wst;
+                    if (p == 0) {  // z enters the sum once; read before the shuffle barrier, written after it
+#pragma unroll
+                        for (int o = 0; o < C; ++o) acc[o] = xt[o * HW + pix];
+                    }
+#pragma unroll
+                    for (int m = 0; m < NTL; ++m) {
+                        if (hs >= tkh[m] && ws >= tkw[m]) {
+                            const float* xs = xt + pix + toff[m];
+#pragma unroll(WREG ? C : (C <= 12 ? 2 : 1))
+                            for (int i = 0; i < C; ++i) {
+                                const float xv = -xs[i * HW];
+                                if constexpr (WREG) {
+#pragma unroll
+                                    for (int o = 0; o < C; ++o) acc[o] = fmaf(xv, wr[m][i][o], acc[o]);
+                                } else if constexpr (CPP % 4 == 0) {
+#pragma unroll
+                                    for (int v = 0; v < CPP / 4; ++v) {
+                                        const float4 f = *reinterpret_cast<const float4*>(wp[m] + i * CPP + 4 * v);
+                                        if (4 * v + 0 < C) acc[4 * v + 0] = fmaf(xv, f.x, acc[4 * v + 0]);
+                                        if (4 * v + 1 < C) acc[4 * v + 1] = fmaf(xv, f.y, acc[4 * v + 1]);
+                                        if (4 * v + 2 < C) acc[4 * v + 2] = fmaf(xv, f.z, acc[4 * v + 2]);
+                                        if (4 * v + 3 < C) acc[4 * v + 3] = fmaf(xv, f.w, acc[4 * v + 3]);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int o = 0; o < C; ++o) acc[o] = fmaf(xv, wp[m][i * CPP + o], acc[o]);
+                                }
+                            }
+                        }
+                    }
+                }
+                // combine the P partial sums of the pixel (all lanes of a pixel share `act`)
+                if constexpr (P > 1) {  // (the shuffles also order the z reads above before the x writes below)
+#pragma unroll
+                    for (int off = 1; off < P; off <<= 1)
+#pragma unroll
+                        for (int o = 0; o < C; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
+                }
+                if (act) {
+                    // corner tap: x[o] = acc[o] - sum_{i<o} W[o,i,corner] x[i]
+#pragma unroll
+                    for (int i = 0; i < C - 1; ++i)
+#pragma unroll
+                        for (int o = i + 1; o < C; ++o) {
+                            if constexpr (CREG) acc[o] = fmaf(-acc[i], wc[i][o], acc[o]);
+                            else acc[o] = fmaf(-acc[i], wg[i * CPP + o], acc[o]);
+                        }
+#pragma unroll
+                    for (int o = 0; o < C; ++o)
+                        if ((o % P) == p) xt[o * HW + pix] = acc[o];
+                    // advance inside the stack
+                    if (++hs == H) { hs = 0; xt += a.tile_stride; }
+                } else if (r < 0) {
+                    ++hs;
+                }
+                ++r;
+                __syncwarp();
+            }
+        }
+
+        if (a.bulk) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                for (int t = 0; t < nt; ++t)
+                    bulk_s2g(a.x + ((long)(n0 + t) * s.G + g) * a.tile_floats, buf + t * a.tile_stride,
+                             (uint32_t)(a.tile_floats * 4));
+                bulk_commit();
+                if (a.S == 3) {
+                    bulk_wait_read_1w();
+                    const long nxt = item + 2 * gstride;
+                    if (nxt < a.n_items) issue_load(nxt, (int)((k + 2) % 3));
+                } else {
+                    bulk_wait_read_all();
+                    const long nxt = item + (long)a.S * gstride;
+                    if (nxt < a.n_items) issue_load(nxt, st);
+                }
+            }
+        } else {
+            for (int t = 0; t < nt; ++t) {
+                float* dst = a.x + ((long)(n0 + t) * s.G + g) * a.tile_floats;
+                for (int e = lane; e < a.tile_floats; e += 32) dst[e] = buf[t * a.tile_stride + e];
+            }
+            __syncwarp();
+        }
+    }
+    if (a.bulk && lane == 0) bulk_wait_all();
+}
+
+template <int C, int KH, int KW, int P>
+int launch_inst(const WaveArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    auto kern = inverse_wave_kernel<C, KH, KW, P>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, threads, smem, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+template <int C, int KH, int KW>
+int dispatch_p(int P, const WaveArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    switch (P) {
+        case 1: return launch_inst<C, KH, KW, 1>(a, grid, threads, smem, st);
+        case 2: return launch_inst<C, KH, KW, 2>(a, grid, threads, smem, st);
+        case 4: return launch_inst<C, KH, KW, 4>(a, grid, threads, smem, st);
+        default: return launch_inst<C, KH, KW, 8>(a, grid, threads, smem, st);
+    }
+}
+
+// per-channel-count dispatch; explicitly instantiated in finc_inverse_wave_c<N>.cu so the
+// instantiations compile in parallel
+template <int C>
+int dispatch_c(int kH, int P, const WaveArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    if (kH == 3) return dispatch_p<C, 3, 3>(P, a, grid, threads, smem, st);
+    return dispatch_p<C, 5, 5>(P, a, grid, threads, smem, st);
+}
+
+}  // namespace wave
+}  // namespace finc

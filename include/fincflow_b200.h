@@ -48,6 +48,7 @@ extern "C" {
 #define FINC_FLAG_NAIVE 1u        /* force the generic one-thread-per-output kernels (testing) */
 #define FINC_FLAG_NO_MASK 2u      /* backward_weight: do NOT apply the FInC gradient mask */
 #define FINC_FLAG_ACCUMULATE 4u   /* backward_weight: dw += result instead of dw = result */
+#define FINC_FLAG_GENERIC_TILED 16u /* inverse: skip the shape-specialised kernel, use the generic tiled one (testing) */
 #define FINC_FLAG_LOGDET_ACCUMULATE 8u /* forward: logdet[n] += ... (FlowSequential's `logdet += layer_logdet`) */
 
 /* error codes (negative); positive return values are cudaError_t */

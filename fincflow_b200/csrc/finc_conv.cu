@@ -1,342 +1,128 @@
-// finc_conv.cu -- fused FInC forward and backward-input convolution for sm_100a.
-//
-// One launch covers a whole [B, G*C, H, W] tensor: all G groups (the four padding corners
-// of a FastFlowUnit), no F.pad copy, no chunk/cat copies (reference:
-// fastflow/fastflow.py:31-50, layers/conv.py:102-107).
-//
-// Execution model ("warp-persistent workers"):
-//   * grid = one CTA per SM (or fewer for tiny problems); every warp is an independent
-//     worker looping over items.  An item is T tiles (n..n+T-1, g) of one group.
-//   * lane 0 of the warp moves the item's tiles HBM -> shared with 1-D TMA bulk copies
-//     completing on a per-warp mbarrier ring (S stages), so loads of the next item overlap
-//     the FMAs of the current one and no CTA-wide barrier is ever needed after start-up.
-//   * the group's weights are transposed once per CTA into shared memory as
-//     wk[g][cin][a][b][cout-block][OBP] so that the OB weights a thread needs for one tap
-//     are one (broadcast) vector load.
-//   * each lane register-blocks OB output channels x WT consecutive pixels of a row and
-//     slides the KW-wide window over a row strip held in registers:
-//     (WT+KW-1) + KW shared loads feed OB*WT*KW FMAs.
-//   * results go straight from registers to global memory with vector stores (adjacent
-//     lanes own adjacent strips, so warps write whole 128-byte lines).
-//
-// Backward-input is the same kernel: dx = conv(dz) with the weights transposed (o<->i),
-// both kernel axes reversed and the opposite padding corner -- all folded into the
-// weight staging, the inner loop is identical.
-//
-// Roofline: HBM-bound for C <= 3 (8 B/element, 2*C*kH*kW flop/element), CUDA-core FFMA
-// bound beyond.
-#include "finc_common.cuh"
+// finc_conv.cu -- host-side planning for the fused FInC forward / backward-input convolution
+// (kernel: finc_conv.cuh; instantiations: finc_conv_c<N>.cu).
+#include "finc_conv.cuh"
 
 namespace finc {
 
+using conv::ConvArgs;
+using conv::kMaxConsumerWarps;
+
 namespace {
 
-constexpr int kMaxWarps = 16;
-
-struct ConvArgs {
-    const float* x;
-    const float* w;
-    float* y;
-    float* logdet;    // nullable; [B], written by CTA (0,0) (forward only)
-    int logdet_acc;   // 1: logdet[n] += value
-    Shape s;
-    int transpose;
-    int T;            // tiles per item
-    int S;            // pipeline stages per warp
-    int nob;          // output-channel blocks
-    int gsplit;       // 1: blockIdx.y selects the group, weights of one group in smem
-    int bulk;         // 1: TMA bulk copies usable (alignment / size)
-    int tile_floats;  // C*H*W
-    int tile_stride;  // smem stride between the T tiles of a stage (>= tile_floats, 16B multiple)
-    int wk_floats;    // weight floats in smem (all groups or one)
-    long n_items;     // per group when gsplit, else over all groups
-};
-
-template <int OB>
-struct ObPad {
-    static constexpr int value = OB <= 2 ? OB : ((OB + 3) / 4) * 4;
-};
-
-template <int OB, int WT, int KW>
-__global__ void __launch_bounds__(kMaxWarps * 32, 1) conv_warp_kernel(const ConvArgs a) {
-    constexpr int OBP = ObPad<OB>::value;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* wk = reinterpret_cast<float*>(smem_raw);
-    const int nwarps = blockDim.x >> 5;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const Shape& s = a.s;
-    const int C = s.C, H = s.H, W = s.W, kH = s.kH;
-    const int HW = H * W;
-    const int stage_floats = a.T * a.tile_stride;
-    float* bufs = wk + ((a.wk_floats + 31) & ~31) + (size_t)warp * a.S * stage_floats;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wk + ((a.wk_floats + 31) & ~31) + (size_t)nwarps * a.S * stage_floats) +
-                     warp * a.S;
-
-    const int g_fixed = a.gsplit ? (int)blockIdx.y : -1;
-    const long gw = (long)warp * gridDim.x + blockIdx.x;  // spread items across SMs first
-    const long gstride = (long)gridDim.x * nwarps;
-    auto item_g = [&](long item) -> int { return a.gsplit ? g_fixed : (int)(item % s.G); };
-    auto item_n0 = [&](long item) -> int { return (int)(a.gsplit ? item : item / s.G) * a.T; };
-
-    auto issue_load = [&](long item, int st) {  // lane 0 only
-        const int g = item_g(item), n0 = item_n0(item);
-        const int nt = min(a.T, s.B - n0);
-        mbar_arrive_expect_tx(&bars[st], (uint32_t)(nt * a.tile_floats * 4));
-        for (int t = 0; t < nt; ++t)
-            bulk_g2s(bufs + st * stage_floats + t * a.tile_stride, a.x + ((long)(n0 + t) * s.G + g) * a.tile_floats,
-                     (uint32_t)(a.tile_floats * 4), &bars[st]);
-    };
-
-    // ---- start-up: barriers + first loads (overlapped with the weight staging) ----------
-    if (a.bulk && lane == 0) {
-        for (int st = 0; st < a.S; ++st) mbar_init(&bars[st], 1);
-        fence_mbar_init();
-        for (int st = 0; st < a.S; ++st) {
-            const long item = gw + st * gstride;
-            if (item < a.n_items) issue_load(item, st);
-        }
-    }
-    {
-        // stage weights: wk[gl][cin][a'][b'][ob][OBP]; zero padding first
-        for (int e = threadIdx.x; e < a.wk_floats; e += blockDim.x) wk[e] = 0.f;
-        __syncthreads();
-        const int kk = kH * KW;
-        const int per_g = C * C * kk;
-        const int ng = a.gsplit ? 1 : s.G;
-        for (int e = threadIdx.x; e < ng * per_g; e += blockDim.x) {
-            const int gl = e / per_g;
-            const int g = a.gsplit ? g_fixed : gl;
-            int r = e - gl * per_g;
-            const int b = r % KW;
-            r /= KW;
-            const int aa = r % kH;
-            r /= kH;
-            const int i = r % C, o = r / C;
-            const float v = a.w[(long)g * per_g + (e - gl * per_g)];
-            int cin, cout, ap, bp;
-            if (!a.transpose) { cin = i; cout = o; ap = aa; bp = b; }
-            else { cin = o; cout = i; ap = kH - 1 - aa; bp = KW - 1 - b; }
-            wk[((((gl * C + cin) * kH + ap) * KW + bp) * a.nob + cout / OB) * OBP + cout % OB] = v;
-        }
-        __syncthreads();
-    }
-
-    // ---- fused logdet epilogue: logdet[n] = H*W*sum_g sum_o log|Ws[g][o][o][a*][b*]| ----------
-    // (reference returns the constant 0.0, layers/conv.py:106; the diagonal is 1 by construction)
-    if (a.logdet != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && warp == 0) {
-        float ld = 0.f;
-        for (int e = lane; e < s.G * C; e += 32) {
-            const int g = e / C, o = e - g * C;
-            const int ord = order_of(s.orders, g);
-            ld += logf(fabsf(a.w[(((long)g * C + o) * C + o) * kH * KW + corner_a(ord, kH) * KW + corner_b(ord, KW)]));
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, off);
-        ld *= (float)H * (float)W;
-        for (int n = lane; n < s.B; n += 32) a.logdet[n] = a.logdet_acc ? a.logdet[n] + ld : ld;
-    }
-
-    const int nstrip = W / WT;
-    const int sub_per_tile = a.nob * H * nstrip;
-
-    long k = 0;
-    for (long item = gw; item < a.n_items; item += gstride, ++k) {
-        const int st = (int)(k % a.S);
-        const int g = item_g(item), n0 = item_n0(item);
-        const int nt = min(a.T, s.B - n0);
-        float* buf = bufs + st * stage_floats;
-        if (a.bulk) {
-            mbar_wait(&bars[st], (uint32_t)((k / a.S) & 1));
-        } else {
-            for (int t = 0; t < nt; ++t) {
-                const float* src = a.x + ((long)(n0 + t) * s.G + g) * a.tile_floats;
-                for (int e = lane; e < a.tile_floats; e += 32) buf[t * a.tile_stride + e] = src[e];
+// output channels per lane, from the blocks instantiated for this channel count
+// (finc_conv_c<N>.cu).  Larger blocks are more FMA-efficient; smaller ones give a small batch
+// enough sub-items to occupy every SM.
+int pick_ob(int ct, int C, long rows_strips_per_tile, long tiles_per_cta) {
+    static const int table[][4] = {{0, 0, 0, 0}};
+    (void)table;
+    int cands[5];
+    int n = 0;
+    switch (ct) {
+        case 1: cands[n++] = 1; break;
+        case 2: cands[n++] = 2; cands[n++] = 1; break;
+        case 3: cands[n++] = 3; cands[n++] = 1; break;
+        case 4: cands[n++] = 4; cands[n++] = 2; break;
+        case 6: cands[n++] = 6; cands[n++] = 3; cands[n++] = 2; break;
+        case 12: case 24: cands[n++] = 4; cands[n++] = 2; break;
+        default:  // generic: any divisor among {6,4,3,2,1}; 4 with a padded last block for C > 6
+            for (int ob : {6, 4, 3, 2, 1}) {
+                if (ob > C) continue;
+                if (C % ob != 0 && !(ob == 4 && C > 6)) continue;
+                if (ob == 6 && C % 4 == 0) continue;
+                cands[n++] = ob;
             }
-            __syncwarp();
-        }
-        const int ord = order_of(s.orders, g) ^ (a.transpose ? 3 : 0);
-        const int r0 = (ord & 2) ? 0 : -(kH - 1);
-        const int c0 = (ord & 1) ? 0 : -(KW - 1);
-        const float* wg = wk + (size_t)(a.gsplit ? 0 : g) * C * kH * KW * a.nob * OBP;
-
-        const int nsub = nt * sub_per_tile;
-        for (int sub = lane; sub < nsub; sub += 32) {
-            int r = sub;
-            const int strip = r % nstrip;
-            r /= nstrip;
-            const int h = r % H;
-            r /= H;
-            const int ob = r % a.nob;
-            const int t = r / a.nob;
-            const int w0 = strip * WT;
-            const float* xt = buf + t * a.tile_stride;
-            float acc[OB][WT];
-#pragma unroll
-            for (int o = 0; o < OB; ++o)
-#pragma unroll
-                for (int q = 0; q < WT; ++q) acc[o][q] = 0.f;
-
-            for (int cin = 0; cin < C; ++cin) {
-                for (int ap = 0; ap < kH; ++ap) {
-                    const int hh = h + r0 + ap;
-                    if (hh < 0 || hh >= H) continue;
-                    const float* xr = xt + cin * HW + hh * W;
-                    float xs[WT + KW - 1];
-#pragma unroll
-                    for (int q = 0; q < WT + KW - 1; ++q) {
-                        const int col = w0 + c0 + q;
-                        xs[q] = (col >= 0 && col < W) ? xr[col] : 0.f;
-                    }
-                    const float* wp = wg + (size_t)((cin * kH + ap) * KW) * a.nob * OBP + ob * OBP;
-#pragma unroll
-                    for (int bp = 0; bp < KW; ++bp) {
-                        float wv[OB];
-                        if constexpr (OBP % 4 == 0) {
-#pragma unroll
-                            for (int v = 0; v < OBP / 4; ++v) {
-                                const float4 f = *reinterpret_cast<const float4*>(wp + bp * a.nob * OBP + 4 * v);
-                                if (4 * v + 0 < OB) wv[4 * v + 0] = f.x;
-                                if (4 * v + 1 < OB) wv[4 * v + 1] = f.y;
-                                if (4 * v + 2 < OB) wv[4 * v + 2] = f.z;
-                                if (4 * v + 3 < OB) wv[4 * v + 3] = f.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int o = 0; o < OB; ++o) wv[o] = wp[bp * a.nob * OBP + o];
-                        }
-#pragma unroll
-                        for (int o = 0; o < OB; ++o)
-#pragma unroll
-                            for (int q = 0; q < WT; ++q) acc[o][q] = fmaf(wv[o], xs[q + bp], acc[o][q]);
-                    }
-                }
-            }
-            float* yt = a.y + ((long)(n0 + t) * s.G + g) * a.tile_floats + h * W + w0;
-#pragma unroll
-            for (int o = 0; o < OB; ++o) {
-                const int oc = ob * OB + o;
-                if (oc < C) {
-                    float* yp = yt + oc * HW;
-                    if constexpr (WT == 4) {
-                        *reinterpret_cast<float4*>(yp) = make_float4(acc[o][0], acc[o][1], acc[o][2], acc[o][3]);
-                    } else if constexpr (WT == 2) {
-                        *reinterpret_cast<float2*>(yp) = make_float2(acc[o][0], acc[o][1]);
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < WT; ++q) yp[q] = acc[o][q];
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        if (a.bulk && lane == 0) {
-            const long nxt = item + (long)a.S * gstride;
-            if (nxt < a.n_items) issue_load(nxt, st);  // all lanes are done reading this stage
-        }
     }
-}
-
-template <int OB, int WT, int KW>
-int launch_inst(const ConvArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    auto kern = conv_warp_kernel<OB, WT, KW>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    kern<<<grid, threads, smem, st>>>(a);
-    return (int)cudaGetLastError();
-}
-
-template <int OB, int WT>
-int dispatch_kw(int KW, const ConvArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st, bool* handled) {
-    *handled = true;
-    switch (KW) {
-        case 2: return launch_inst<OB, WT, 2>(a, grid, threads, smem, st);
-        case 3: return launch_inst<OB, WT, 3>(a, grid, threads, smem, st);
-        case 5: return launch_inst<OB, WT, 5>(a, grid, threads, smem, st);
-        default: *handled = false; return 0;
+    int best = cands[n - 1];
+    for (int i = 0; i < n; ++i) {
+        const long subs = tiles_per_cta * ((C + cands[i] - 1) / cands[i]) * rows_strips_per_tile;
+        if (subs >= 384 || tiles_per_cta >= 64) return cands[i];
     }
+    return best;
 }
 
-template <int OB>
-int dispatch_wt(int WT, int KW, const ConvArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st,
-                bool* handled) {
-    switch (WT) {
-        case 4: return dispatch_kw<OB, 4>(KW, a, grid, threads, smem, st, handled);
-        case 2: return dispatch_kw<OB, 2>(KW, a, grid, threads, smem, st, handled);
-        default: return dispatch_kw<OB, 1>(KW, a, grid, threads, smem, st, handled);
-    }
-}
-
-int pick_ob(int C) {
-    if (C <= 4) return C;
-    if (C % 6 == 0 && C % 4 != 0) return 6;  // C = 6, 18, ...
-    if (C % 4 == 0) return 4;
-    if (C % 3 == 0) return 3;
-    return 4;  // padded last block
-}
+unsigned magic(unsigned d) { return d <= 1 ? 0u : (unsigned)(((1ull << 32) + d - 1) / d); }
 
 }  // namespace
 
 int launch_conv_fast(const float* x, const float* w, float* y, float* logdet, bool logdet_acc, const Shape& s,
                      bool transpose, cudaStream_t st, bool* handled) {
     *handled = false;
-    if (s.kW != 2 && s.kW != 3 && s.kW != 5) return 0;
+    if (!(s.kH == s.kW && (s.kH == 3 || s.kH == 5 || s.kH == 2))) return 0;
     const long tile_floats_l = (long)s.C * s.H * s.W;
-    if (tile_floats_l * 4 > 64 * 1024) return 0;
+    if (tile_floats_l * 4 > 48 * 1024) return 0;
     ConvArgs a{};
-    a.x = x; a.w = w; a.y = y; a.logdet = transpose ? nullptr : logdet; a.logdet_acc = logdet_acc ? 1 : 0; a.s = s; a.transpose = transpose ? 1 : 0;
+    a.x = x; a.w = w; a.y = y; a.logdet = transpose ? nullptr : logdet; a.logdet_acc = logdet_acc ? 1 : 0;
+    a.s = s; a.transpose = transpose ? 1 : 0;
     a.tile_floats = (int)tile_floats_l;
-    const int OB = pick_ob(s.C);
+    a.bulk = (a.tile_floats % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    int WT = 1;
+    const bool y16 = (reinterpret_cast<uintptr_t>(y) & 15) == 0, y8 = (reinterpret_cast<uintptr_t>(y) & 7) == 0;
+    if (s.W % 4 == 0 && y16) WT = 4;  // smem rows are 16-byte aligned because tile_floats % 4 == 0 when W % 4 == 0
+    else if (s.W % 2 == 0 && y8 && (a.tile_floats % 2 == 0)) WT = 2;
+    a.nstrip = s.W / WT;
+    // channel-count specialisation (3x3 / 5x5, vector strips); everything else is the generic C
+    int ct = 0;
+    if ((s.kH == 3 || s.kH == 5) && WT >= 2)
+        for (int c : {1, 2, 3, 4, 6, 12, 24})
+            if (s.C == c) ct = c;
+    const int sms = sm_count_cached();
+    const size_t smem_max = max_optin_smem_cached();
+    const size_t budget = smem_max > 8192 ? smem_max - 4096 : 0;
+    // group split only when the weights of all groups cannot share the CTA's shared memory
+    a.gsplit = ((size_t)s.G * s.C * s.C * s.kH * s.kW * 4 * 4 / 3 > budget / 2) ? 1 : 0;
+    const long n_tiles = a.gsplit ? s.B : (long)s.B * s.G;
+    long ctas_max = a.gsplit ? sms / s.G : sms;
+    if (ctas_max < 1) ctas_max = 1;
+    const long spread = (n_tiles + ctas_max - 1) / ctas_max;
+    const int OB = pick_ob(ct, s.C, (long)s.H * a.nstrip, spread);
     const int OBP = OB <= 2 ? OB : ((OB + 3) / 4) * 4;
     a.nob = (s.C + OB - 1) / OB;
     const size_t wk_per_g = (size_t)s.C * s.kH * s.kW * a.nob * OBP;
-    const size_t smem_max = max_optin_smem_cached();
-    const size_t budget = smem_max > 8192 ? smem_max - 4096 : 0;
-    if (wk_per_g * s.G * 4 <= budget / 2) { a.gsplit = 0; a.wk_floats = (int)(wk_per_g * s.G); }
-    else if (wk_per_g * 4 <= budget / 2) { a.gsplit = 1; a.wk_floats = (int)wk_per_g; }
-    else return 0;
+    a.wk_floats = (int)(a.gsplit ? wk_per_g : wk_per_g * s.G);
+    if ((size_t)a.wk_floats * 4 > budget / 2) return 0;
+    const int sub_per_tile = a.nob * s.H * a.nstrip;
+    if ((long)sub_per_tile >= 65536) return 0;
+    a.m_nstrip = magic(a.nstrip); a.m_h = magic(s.H); a.m_nob = magic(a.nob);
 
-    a.bulk = (a.tile_floats % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-    // vector width of the output stores / strip width
-    int WT = 1;
-    const bool y16 = (reinterpret_cast<uintptr_t>(y) & 15) == 0, y8 = (reinterpret_cast<uintptr_t>(y) & 7) == 0;
-    if (s.W % 4 == 0 && y16) WT = 4;
-    else if (s.W % 2 == 0 && y8 && (a.tile_floats % 2 == 0)) WT = 2;
-
-    const int sms = sm_count_cached();
-    const long tiles_per_g = s.B;
-    // tiles per item: keep >= ~8 items per SM when the batch allows, <= 8 KB per stage
-    int T = 8;
-    while (T > 1 && (((tiles_per_g + T - 1) / T) * s.G < (long)sms * 8 || (long)T * a.tile_floats * 4 > 8 * 1024)) T >>= 1;
-    a.T = T;
-    a.tile_stride = (a.tile_floats + 3) & ~3;
-    a.S = 2;
-    const size_t wk_bytes = (size_t)((a.wk_floats + 31) & ~31) * 4;
-    size_t per_warp = (size_t)a.S * a.T * a.tile_stride * 4 + a.S * 8;
-    int nwarps = (int)((budget - wk_bytes) / per_warp);
-    if (nwarps < 2) {
-        a.S = 1;
-        per_warp = (size_t)a.T * a.tile_stride * 4 + 8;
-        nwarps = (int)((budget - wk_bytes) / per_warp);
-        if (nwarps < 1) return 0;
-    }
-    if (nwarps > kMaxWarps) nwarps = kMaxWarps;
-    const int nbT = (s.B + a.T - 1) / a.T;
-    a.n_items = a.gsplit ? nbT : (long)nbT * s.G;
-    // do not launch more warps than items
-    long ctas = a.gsplit ? sms / s.G : sms;
-    if (ctas < 1) ctas = 1;
-    if (ctas > a.n_items) ctas = a.n_items;
-    while (nwarps > 1 && (long)(nwarps - 1) * ctas >= a.n_items) --nwarps;
-    const size_t smem = wk_bytes + (size_t)nwarps * per_warp + 16;
+    // chunk: about one sub-item per consumer thread (512), at most 24 KB, and small enough that
+    // every SM gets a chunk when the batch is small
+    int CH = (kMaxConsumerWarps * 32 + sub_per_tile - 1) / sub_per_tile;
+    while (CH > 1 && (long)CH * a.tile_floats * 4 > 24 * 1024) --CH;
+    if (CH > spread) CH = (int)spread;
+    if (CH > s.B) CH = s.B;
+    if (CH < 1) CH = 1;
+    if ((long)CH * sub_per_tile >= 65536) return 0;
+    a.CH = CH;
+    a.nblk = (s.B + CH - 1) / CH;
+    a.n_chunks = a.gsplit ? a.nblk : (long)a.nblk * s.G;
+    long ctas = ctas_max < a.n_chunks ? ctas_max : a.n_chunks;
+    const long chunks_per_cta = (a.n_chunks + ctas - 1) / ctas;
+    const size_t wk_bytes = (size_t)(((a.wk_floats + 31) & ~31) + conv::kFrontPad) * 4;
+    const size_t stage_bytes = (size_t)CH * a.tile_floats * 4;
+    int S = (int)(chunks_per_cta < 3 ? chunks_per_cta : 3);
+    while (S > 1 && wk_bytes + S * stage_bytes + 256 > budget) --S;
+    if (wk_bytes + S * stage_bytes + 256 > budget) return 0;
+    a.S = S;
+    int cw = (CH * sub_per_tile + 31) / 32;
+    if (cw > kMaxConsumerWarps) cw = kMaxConsumerWarps;
+    if (cw < 1) cw = 1;
+    const size_t smem = wk_bytes + S * stage_bytes + 32 + 2 * S * 8 + 64;
     dim3 grid((unsigned)ctas, a.gsplit ? s.G : 1, 1);
-    switch (OB) {
-        case 1: return dispatch_wt<1>(WT, s.kW, a, grid, nwarps * 32, smem, st, handled);
-        case 2: return dispatch_wt<2>(WT, s.kW, a, grid, nwarps * 32, smem, st, handled);
-        case 3: return dispatch_wt<3>(WT, s.kW, a, grid, nwarps * 32, smem, st, handled);
-        case 4: return dispatch_wt<4>(WT, s.kW, a, grid, nwarps * 32, smem, st, handled);
-        case 6: return dispatch_wt<6>(WT, s.kW, a, grid, nwarps * 32, smem, st, handled);
-        default: return 0;
+    const int threads = (cw + 1) * 32;
+    int rc;
+    switch (ct) {
+        case 1: rc = conv::dispatch_ob<1>(OB, WT, s.kH, a, grid, threads, smem, st); break;
+        case 2: rc = conv::dispatch_ob<2>(OB, WT, s.kH, a, grid, threads, smem, st); break;
+        case 3: rc = conv::dispatch_ob<3>(OB, WT, s.kH, a, grid, threads, smem, st); break;
+        case 4: rc = conv::dispatch_ob<4>(OB, WT, s.kH, a, grid, threads, smem, st); break;
+        case 6: rc = conv::dispatch_ob<6>(OB, WT, s.kH, a, grid, threads, smem, st); break;
+        case 12: rc = conv::dispatch_ob<12>(OB, WT, s.kH, a, grid, threads, smem, st); break;
+        case 24: rc = conv::dispatch_ob<24>(OB, WT, s.kH, a, grid, threads, smem, st); break;
+        default: rc = conv::dispatch_ob<0>(OB, WT, s.kH, a, grid, threads, smem, st); break;
     }
+    if (rc == FINC_E_UNSUPPORTED) return 0;  // not instantiated: let the generic kernels take it
+    *handled = true;
+    return rc;
 }
 
 }  // namespace finc

@@ -181,8 +181,7 @@ def kernel_detail(torch, _native, dev, peak):
             dz = torch.randn_like(x)
             y = torch.empty_like(x)
             dw = torch.empty_like(w)
-            ws = torch.empty(_native.backward_weight_workspace_bytes(B, 4, CT // 4, H, W, KSIZE, KSIZE),
-                             dtype=torch.uint8, device=dev)
+            ws = _native.new_workspace(_native.backward_weight_workspace_bytes(B, 4, CT // 4, H, W, KSIZE, KSIZE), dev)
             fns = {
                 "forward_logdet": lambda: _native.forward(x, w, out=y, want_logdet=False),
                 "backward_input": lambda: _native.backward_input(dz, w, out=y),

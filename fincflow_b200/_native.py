@@ -23,6 +23,7 @@ FLAG_NO_MASK = 2
 FLAG_ACCUMULATE = 4
 FLAG_LOGDET_ACCUMULATE = 8
 FLAG_GENERIC_TILED = 16
+FLAG_WORKSPACE_CLEAN = 32
 
 # every symbol declared in include/fincflow_b200.h
 SYMBOLS = (
@@ -151,6 +152,12 @@ def backward_weight_workspace_bytes(B, G, C, H, W, kH, kW) -> int:
     return int(load().finc_backward_weight_workspace_bytes(B, G, C, H, W, kH, kW))
 
 
+def new_workspace(nbytes, device):
+    """zero-initialised workspace for backward_weight(workspace=...); the kernels leave its
+    ticket counters zero, so it can be reused by stream-ordered calls without a memset"""
+    return torch.zeros(max(int(nbytes), 4096), dtype=torch.uint8, device=device)
+
+
 def backward_weight(dz, x, ksize, G=4, orders=ORDERS_UNIT, flags=0, out=None, workspace=None):
     """Masked dW [G*C, C, kH, kW] (FLAG_NO_MASK for the raw gradient).  `out` may be a view
     into a flat gradient bucket; FLAG_ACCUMULATE adds into it."""
@@ -168,7 +175,8 @@ def backward_weight(dz, x, ksize, G=4, orders=ORDERS_UNIT, flags=0, out=None, wo
         nbytes = lib.finc_backward_weight_workspace_bytes(B, G, C, H, W, kH, kW)
         ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=x.device)
     else:
-        ws = workspace
+        ws = workspace  # caller-owned, zero-initialised once (see new_workspace): skips the memset node
+        flags |= FLAG_WORKSPACE_CLEAN
     _check(lib.finc_backward_weight_f32(dz.data_ptr(), x.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
                                         B, G, C, H, W, kH, kW, orders, flags, _stream(x)),
            "finc_backward_weight_f32")

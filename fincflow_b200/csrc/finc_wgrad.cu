@@ -7,26 +7,31 @@
 // (layers/conv.py:98-99, train/experiment.py:16-18,250).  The result can be written
 // straight into a flat gradient bucket (the NCCL all-reduce buffer).
 //
-// Design: a long reduction (B*H*W terms) into few outputs (C*C*kH*kW per group).
-//   * grid = (X, G, Z): CTA (x, g, z) streams every X-th chunk of `ipc` images of group g
-//     (x and dz tiles, TMA bulk copies, 2-stage mbarrier pipeline) and owns the output
-//     slice z of the group.
-//   * output-stationary: warp <-> (input channel i, block of OBW output channels o,
-//     row-split slot); lane <-> (column w, row phase).  Each lane keeps
-//     OBW*kH*kW accumulators in registers for the whole kernel: per pixel OBW + kH*kW
-//     conflict-free shared loads feed OBW*kH*kW FMAs.
-//   * reduction is deterministic: xor-shuffle tree inside the warp, fixed-order sums over
-//     the row-split warps (shared) and over the X CTAs (global partials; the last CTA to
-//     finish, found with one atomic ticket per (g,z), does the final pass, applies the
-//     mask and writes dw).  No floating-point atomics anywhere.
+// A long reduction (B*H*W terms) into few outputs (C*C*kH*kW per group):
+//   * grid = (X, G, Z): CTA (x, g, z) streams every X-th chunk of CH images of group g -- the
+//     x and dz tiles, 2*CH TMA bulk copies per chunk on a full/empty mbarrier ring fed by a
+//     producer warp -- and owns the (input channel, output block) combos of slice z.
+//   * output-stationary lanes: a lane owns one combo (i, OB output channels) and one slot
+//     (tile of the chunk, WT-wide column strip, row range); it keeps OB*kH*kW accumulators
+//     in registers for the whole kernel.  Sweeping its rows it holds a sliding window of kH
+//     input row strips in registers (one new row = two vector loads per step, rotated at
+//     compile time) and loads OB dz strips: (2 + OB) shared loads feed OB*kH*kW*WT FMAs.
+//     Rows / halos outside the image are redirected to a zero strip (no branches).
+//   * deterministic reduction: segmented xor-shuffle over the slots of a combo, fixed-order
+//     sums over warps (shared) and over the X CTAs (global partials; the last CTA to finish,
+//     found with one atomic ticket per (g,z), applies the mask and writes dw).  No
+//     floating-point atomics anywhere.
 #include "finc_common.cuh"
 
 namespace finc {
 
 namespace {
 
-constexpr int kWarps = 12;
+constexpr int kMaxConsumerWarps = 16;
+// accumulators + window + dz strips of an OB=6 lane need ~150 registers: 12 consumer warps
+constexpr int max_consumer_warps(int ob, int kh) { return (ob >= 6 || (kh >= 5 && ob >= 2)) ? 12 : kMaxConsumerWarps; }
 constexpr int kCounterBytes = 4096;
+constexpr int kFrontPad = 32;
 
 struct WgArgs {
     const float* dz;
@@ -36,161 +41,252 @@ struct WgArgs {
     unsigned* counters;
     Shape s;
     unsigned flags;
-    int ipc;
-    int tile_floats;
-    int tile_stride;
-    int bulk;
-    int nobw;
-    int jpc;   // jobs per CTA
-    int rsw;   // row-split warps per job
-    int X;
-    int Z;
-    int nchunks;
+    int CH, S, bulk, tile_floats;
+    int nob, nstrip, RR, rpr;  // output blocks, strips per row, row ranges per tile, rows per range
+    int slots, SP;             // slots per combo and its padded size (power of two <= 32, or multiple of 32)
+    int ncombo, cpc;           // combos in total / per CTA
+    int X, Z, nchunks;
+    unsigned m_nstrip, m_rr;
 };
 
-template <int OBW, int KH, int KW>
-__global__ void __launch_bounds__(kWarps * 32, 1) wgrad_kernel(const WgArgs a) {
-    constexpr int NACC = OBW * KH * KW;
+__device__ __forceinline__ unsigned fastdiv(unsigned n, unsigned m) { return m ? __umulhi(n, m) : n; }
+
+template <int N>
+__device__ __forceinline__ void ldn(const float* p, float* out) {
+    if constexpr (N == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+    } else if constexpr (N == 2) {
+        const float2 v = *reinterpret_cast<const float2*>(p);
+        out[0] = v.x; out[1] = v.y;
+    } else {
+        out[0] = p[0];
+    }
+}
+
+template <int WT, int HALO>
+__device__ __forceinline__ void ld_halo(const float* p, float* out) {
+    if constexpr (WT == 4 && HALO == 4) { ldn<4>(p, out); }
+    else {
+#pragma unroll
+        for (int q = 0; q < HALO; q += 2) ldn<2>(p + q, out + q);
+    }
+}
+
+// strip of x row hh (WT + HALO floats starting at column w0 - HALO (left padded) or w0)
+template <int WT, int HALO, bool RIGHT>
+__device__ __forceinline__ void load_row(const float* __restrict__ xc, const float* __restrict__ zrow, int hh, int H,
+                                         int W, int w0, float* out) {
+    const bool ok = hh >= 0 && hh < H;
+    const float* row = xc + hh * W + w0;
+    const bool hok = ok && (RIGHT ? (w0 + WT < W) : (w0 > 0));
+    const float* mp = ok ? row : zrow;
+    const float* hp = hok ? (RIGHT ? row + WT : row - HALO) : zrow;
+    if constexpr (RIGHT) {
+        ldn<WT>(mp, out);
+        ld_halo<WT, HALO>(hp, out + WT);
+    } else {
+        ld_halo<WT, HALO>(hp, out);
+        ldn<WT>(mp, out + HALO);
+    }
+}
+
+template <int OB, int WT, int KH, int KW, bool RIGHT>
+__device__ __forceinline__ void sweep(float (&acc)[OB][KH][KW], const float* __restrict__ xc,
+                                      const float* __restrict__ dzc, const float* __restrict__ zrow, int nvalid_o,
+                                      int H, int W, int HW, int w0, int r0, int h0, int h1) {
+    constexpr int HALO = KW - 1;
+    float win[KH][WT + HALO];
+    // rows h0+r0 .. h0+r0+KH-2 of the window; the last row is loaded inside the step
+#pragma unroll
+    for (int a = 0; a < KH - 1; ++a) load_row<WT, HALO, RIGHT>(xc, zrow, h0 + r0 + a, H, W, w0, win[a]);
+    for (int hb = h0; hb < h1; hb += KH) {
+#pragma unroll
+        for (int rot = 0; rot < KH; ++rot) {
+            const int h = hb + rot;
+            if (h < h1) {
+                // window row for tap a lives in win[(a + rot) % KH]
+                load_row<WT, HALO, RIGHT>(xc, zrow, h + r0 + KH - 1, H, W, w0, win[(KH - 1 + rot) % KH]);
+                float dzv[OB][WT];
+#pragma unroll
+                for (int o = 0; o < OB; ++o) {
+                    const float* dp = (o < nvalid_o) ? dzc + o * HW + h * W + w0 : zrow;
+                    ldn<WT>(dp, dzv[o]);
+                }
+#pragma unroll
+                for (int a = 0; a < KH; ++a)
+#pragma unroll
+                    for (int b = 0; b < KW; ++b)
+#pragma unroll
+                        for (int o = 0; o < OB; ++o)
+#pragma unroll
+                            for (int q = 0; q < WT; ++q)
+                                acc[o][a][b] = fmaf(dzv[o][q], win[(a + rot) % KH][q + b], acc[o][a][b]);
+            }
+        }
+    }
+}
+
+template <int OB, int WT, int KH, int KW>
+__global__ void __launch_bounds__((max_consumer_warps(OB, KH) + 1) * 32, 1) wgrad_kernel(const WgArgs a) {
+    constexpr int NACC = OB * KH * KW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const Shape& s = a.s;
     const int C = s.C, H = s.H, W = s.W, HW = H * W;
-    const int half = a.ipc * a.tile_stride;  // floats of x (or dz) tiles per stage
-    float* stage0 = reinterpret_cast<float*>(smem_raw);
-    float* red = stage0 + 4 * (size_t)half;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(red + kWarps * NACC + (((kWarps * NACC) & 1) ? 1 : 0));
+    float* front = reinterpret_cast<float*>(smem_raw);  // kFrontPad zero floats
+    float* zrow = front + 8;
+    float* bufs = front + kFrontPad;
+    const int half = a.CH * a.tile_floats;  // floats of x (or dz) tiles per stage
+    float* red = bufs + (size_t)a.S * 2 * half + 8;
+    const int nthreads_c = blockDim.x - 32;
+    const int nseg_max = nthreads_c / (a.SP < 32 ? a.SP : 32);
+    uint64_t* full = reinterpret_cast<uint64_t*>(red + ((nseg_max * NACC + 1) & ~1));
+    uint64_t* empty = full + a.S;
     __shared__ int s_last;
 
     const int g = blockIdx.y, zz = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int njobs = C * a.nobw;
-    const int jl_cta = warp / a.rsw, rs = warp - jl_cta * a.rsw;
-    const int job = zz * a.jpc + jl_cta;
-    const bool job_on = jl_cta < a.jpc && job < njobs;
-    const int ci = job_on ? job / a.nobw : 0;
-    const int obw = job_on ? job - ci * a.nobw : 0;
+    const bool is_producer = warp == (nthreads_c >> 5);
     const int ord = order_of(s.orders, g);
+    const bool right = (ord & 1) != 0;
+    const int r0 = (ord & 2) ? 0 : -(KH - 1);
 
-    const int WL = W < 32 ? W : 32;
-    const int HS = W <= 32 ? 32 / W : 1;
-    const int hsl = lane / WL, jl = lane - hsl * WL;
-    const bool lane_on = job_on && hsl < HS;
-    const int ncb = (W + 31) / 32;
-
-    auto issue = [&](int chunk, int st) {  // thread 0 only
-        const int n0 = chunk * a.ipc;
-        const int nt = min(a.ipc, s.B - n0);
-        mbar_arrive_expect_tx(&bars[st], (uint32_t)(2 * nt * a.tile_floats * 4));
-        float* xs = stage0 + (size_t)st * 2 * half;
+    auto issue = [&](int chunk, int st) {  // one elected thread
+        const int n0 = chunk * a.CH;
+        const int nt = min(a.CH, s.B - n0);
+        mbar_arrive_expect_tx(&full[st], (uint32_t)(2 * nt * a.tile_floats * 4));
+        float* xs = bufs + (size_t)st * 2 * half;
         float* ds = xs + half;
         for (int t = 0; t < nt; ++t) {
             const long off = ((long)(n0 + t) * s.G + g) * a.tile_floats;
-            bulk_g2s(xs + t * a.tile_stride, a.x + off, (uint32_t)(a.tile_floats * 4), &bars[st]);
-            bulk_g2s(ds + t * a.tile_stride, a.dz + off, (uint32_t)(a.tile_floats * 4), &bars[st]);
+            bulk_g2s(xs + t * a.tile_floats, a.x + off, (uint32_t)(a.tile_floats * 4), &full[st]);
+            bulk_g2s(ds + t * a.tile_floats, a.dz + off, (uint32_t)(a.tile_floats * 4), &full[st]);
         }
     };
 
-    if (a.bulk && threadIdx.x == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+    if (a.bulk && is_producer && lane == 0) {
+        for (int st = 0; st < a.S; ++st) {
+            mbar_init(&full[st], 1);
+            mbar_init(&empty[st], nthreads_c >> 5);
+        }
         fence_mbar_init();
-        if ((int)blockIdx.x < a.nchunks) issue(blockIdx.x, 0);
-        if ((int)blockIdx.x + a.X < a.nchunks) issue(blockIdx.x + a.X, 1);
+        for (int st = 0; st < a.S; ++st) {
+            const int chunk = blockIdx.x + st * a.X;
+            if (chunk < a.nchunks) issue(chunk, st);
+        }
     }
+    if (threadIdx.x < kFrontPad) front[threadIdx.x] = 0.f;
     __syncthreads();
 
-    float acc[OBW][KH][KW];
-#pragma unroll
-    for (int o = 0; o < OBW; ++o)
-#pragma unroll
-        for (int aa = 0; aa < KH; ++aa)
-#pragma unroll
-            for (int b = 0; b < KW; ++b) acc[o][aa][b] = 0.f;
-
-    int kk = 0;
-    for (int chunk = blockIdx.x; chunk < a.nchunks; chunk += a.X, ++kk) {
-        const int st = kk & 1;
-        const int n0 = chunk * a.ipc;
-        const int nt = min(a.ipc, s.B - n0);
-        float* xs = stage0 + (size_t)st * 2 * half;
-        float* ds = xs + half;
-        if (a.bulk) {
-            mbar_wait(&bars[st], (uint32_t)((kk >> 1) & 1));
-        } else {
-            for (int t = 0; t < nt; ++t) {
-                const long off = ((long)(n0 + t) * s.G + g) * a.tile_floats;
-                for (int e = threadIdx.x; e < a.tile_floats; e += blockDim.x) {
-                    xs[t * a.tile_stride + e] = a.x[off + e];
-                    ds[t * a.tile_stride + e] = a.dz[off + e];
-                }
+    if (is_producer) {
+        if (a.bulk && lane == 0) {
+            int k = a.S;
+            for (int chunk = blockIdx.x + a.S * a.X; chunk < a.nchunks; chunk += a.X, ++k) {
+                const int st = k % a.S;
+                mbar_wait(&empty[st], (uint32_t)(((k / a.S) - 1) & 1));
+                issue(chunk, st);
             }
-            __syncthreads();
         }
-        if (lane_on) {
-            const int R = nt * H;
-            for (int r = rs * HS + hsl; r < R; r += a.rsw * HS) {
-                const int t = r / H, h = r - t * H;
-                const float* xt = xs + t * a.tile_stride + ci * HW;
-                const float* dt = ds + t * a.tile_stride + (obw * OBW) * HW + h * W;
-                for (int cb = 0; cb < ncb; ++cb) {
-                    const int w = cb * 32 + jl;
-                    if (w >= W) break;
-                    float dzv[OBW];
+    } else {
+        // ---- consumers: lane <-> (combo, slot) -------------------------------------------------------
+        const int cl = threadIdx.x / a.SP;            // combo slot inside the CTA
+        const int slot = threadIdx.x - cl * a.SP;
+        const int combo = zz * a.cpc + cl;
+        const bool lane_on = cl < a.cpc && combo < a.ncombo && slot < a.slots;
+        const int ci = lane_on ? combo / a.nob : 0;
+        const int ob = lane_on ? combo - ci * a.nob : 0;
+        unsigned q1 = fastdiv((unsigned)slot, a.m_nstrip);
+        const int strip = slot - (int)q1 * a.nstrip;
+        const unsigned q2 = fastdiv(q1, a.m_rr);
+        const int rr = (int)q1 - (int)q2 * a.RR;
+        const int t = (int)q2;
+        const int w0 = strip * WT;
+        const int h0 = rr * a.rpr, h1 = min(H, h0 + a.rpr);
+        const int nvalid_o = min(OB, C - ob * OB);
+
+        float acc[OB][KH][KW];
 #pragma unroll
-                    for (int o = 0; o < OBW; ++o) dzv[o] = (obw * OBW + o < C) ? dt[o * HW + w] : 0.f;
+        for (int o = 0; o < OB; ++o)
 #pragma unroll
-                    for (int aa = 0; aa < KH; ++aa) {
-                        const int hh = h + row_off(ord, aa, KH);
-                        if (hh < 0 || hh >= H) continue;
+            for (int aa = 0; aa < KH; ++aa)
 #pragma unroll
-                        for (int b = 0; b < KW; ++b) {
-                            const int wc = w + col_off(ord, b, KW);
-                            const float xv = (wc >= 0 && wc < W) ? xt[hh * W + wc] : 0.f;
-#pragma unroll
-                            for (int o = 0; o < OBW; ++o) acc[o][aa][b] = fmaf(dzv[o], xv, acc[o][aa][b]);
-                        }
+                for (int b = 0; b < KW; ++b) acc[o][aa][b] = 0.f;
+
+        int k = 0;
+        for (int chunk = blockIdx.x; chunk < a.nchunks; chunk += a.X, ++k) {
+            const int st = k % a.S;
+            const int n0 = chunk * a.CH;
+            const int nt = min(a.CH, s.B - n0);
+            float* xs = bufs + (size_t)st * 2 * half;
+            float* ds = xs + half;
+            if (a.bulk) {
+                mbar_wait(&full[st], (uint32_t)((k / a.S) & 1));
+            } else {
+                asm volatile("bar.sync 1, %0;" ::"r"(nthreads_c) : "memory");
+                for (int tt = 0; tt < nt; ++tt) {
+                    const long off = ((long)(n0 + tt) * s.G + g) * a.tile_floats;
+                    for (int e = threadIdx.x; e < a.tile_floats; e += nthreads_c) {
+                        xs[tt * a.tile_floats + e] = a.x[off + e];
+                        ds[tt * a.tile_floats + e] = a.dz[off + e];
                     }
                 }
+                asm volatile("bar.sync 1, %0;" ::"r"(nthreads_c) : "memory");
+            }
+            if (lane_on && t < nt && h0 < h1) {
+                const float* xc = xs + t * a.tile_floats + ci * HW;
+                const float* dzc = ds + t * a.tile_floats + (ob * OB) * HW;
+                if (right) sweep<OB, WT, KH, KW, true>(acc, xc, dzc, zrow, nvalid_o, H, W, HW, w0, r0, h0, h1);
+                else sweep<OB, WT, KH, KW, false>(acc, xc, dzc, zrow, nvalid_o, H, W, HW, w0, r0, h0, h1);
+            }
+            if (a.bulk) {
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[st])) : "memory");
             }
         }
-        __syncthreads();  // everyone is done with this stage
-        if (a.bulk && threadIdx.x == 0 && chunk + 2 * a.X < a.nchunks) issue(chunk + 2 * a.X, st);
-    }
 
-    // ---- deterministic reduction: lanes -> warp, row-split warps -> CTA, CTAs -> dw --------
+        // ---- lanes of a combo -> one value per segment (segment = min(SP,32) consecutive lanes) ------
+        const int SPw = a.SP < 32 ? a.SP : 32;
+        const int seg = threadIdx.x / SPw;
 #pragma unroll
-    for (int o = 0; o < OBW; ++o)
+        for (int o = 0; o < OB; ++o)
 #pragma unroll
-        for (int aa = 0; aa < KH; ++aa)
+            for (int aa = 0; aa < KH; ++aa)
 #pragma unroll
-            for (int b = 0; b < KW; ++b) {
-                float v = acc[o][aa][b];
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                if (lane == 0) red[warp * NACC + (o * KH + aa) * KW + b] = v;
-            }
+                for (int b = 0; b < KW; ++b) {
+                    float v = acc[o][aa][b];
+                    for (int off = 1; off < SPw; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                    if ((threadIdx.x & (SPw - 1)) == 0) red[seg * NACC + (o * KH + aa) * KW + b] = v;
+                }
+    }
     __syncthreads();
 
-    const long nout = (long)s.G * C * C * KH * KW;
+    // ---- segments -> CTA value per output (fixed order), then CTAs -> dw ----------------------------
+    // partial slices are stored in CTA-local order [x][g][z][cl*NACC + idx]: coalesced both ways
     const int ca = corner_a(ord, KH), cbn = corner_b(ord, KW);
+    const int segs_per_combo = a.SP <= 32 ? 1 : a.SP / 32;
     const bool direct = a.X == 1;
-    for (int e = threadIdx.x; e < a.jpc * NACC; e += blockDim.x) {
-        const int jj = e / NACC, idx = e - jj * NACC;
-        const int jb = zz * a.jpc + jj;
-        if (jb >= njobs) continue;
-        float v = 0.f;
-        for (int r = 0; r < a.rsw; ++r) v += red[(jj * a.rsw + r) * NACC + idx];
-        const int i = jb / a.nobw, ob = jb - i * a.nobw;
-        const int o = ob * OBW + idx / (KH * KW);
-        if (o >= C) continue;
+    const int nloc = a.cpc * NACC;
+    const long slice = ((long)g * a.Z + zz) * nloc;
+    const long xstride = (long)s.G * a.Z * nloc;
+    auto finish = [&](int l, float v) {
+        const int cl = l / NACC, idx = l - cl * NACC;
+        const int combo = zz * a.cpc + cl;
+        if (combo >= a.ncombo) return;
+        const int i = combo / a.nob, ob = combo - i * a.nob;
+        const int o = ob * OB + idx / (KH * KW);
+        if (o >= C) return;
         const int ab = idx % (KH * KW);
         const long out = (((long)g * C + o) * C + i) * KH * KW + ab;
-        if (direct) {
-            if (!(a.flags & FINC_FLAG_NO_MASK) && ab == ca * KW + cbn && i >= o) v = 0.f;
-            if (a.flags & FINC_FLAG_ACCUMULATE) v += a.dw[out];
-            a.dw[out] = v;
-        } else {
-            a.partial[(long)blockIdx.x * nout + out] = v;
-        }
+        if (!(a.flags & FINC_FLAG_NO_MASK) && ab == ca * KW + cbn && i >= o) v = 0.f;
+        if (a.flags & FINC_FLAG_ACCUMULATE) v += a.dw[out];
+        a.dw[out] = v;
+    };
+    for (int l = threadIdx.x; l < nloc; l += blockDim.x) {
+        const int cl = l / NACC;
+        float v = 0.f;
+        for (int r = 0; r < segs_per_combo; ++r) v += red[(cl * segs_per_combo + r) * NACC + (l - cl * NACC)];
+        if (direct) finish(l, v);
+        else a.partial[(long)blockIdx.x * xstride + slice + l] = v;
     }
     if (direct) return;
 
@@ -203,135 +299,172 @@ __global__ void __launch_bounds__(kWarps * 32, 1) wgrad_kernel(const WgArgs a) {
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int e = threadIdx.x; e < a.jpc * NACC; e += blockDim.x) {
-        const int jj = e / NACC, idx = e - jj * NACC;
-        const int jb = zz * a.jpc + jj;
-        if (jb >= njobs) continue;
-        const int i = jb / a.nobw, ob = jb - i * a.nobw;
-        const int o = ob * OBW + idx / (KH * KW);
-        if (o >= C) continue;
-        const int ab = idx % (KH * KW);
-        const long out = (((long)g * C + o) * C + i) * KH * KW + ab;
+    // the last CTA of (g, z) sums the X slices per output in fixed order (independent coalesced loads)
+    for (int l = threadIdx.x; l < nloc; l += blockDim.x) {
+        const float* pp = a.partial + slice + l;
         float v = 0.f;
-        for (int xx = 0; xx < a.X; ++xx) v += __ldcg(&a.partial[(long)xx * nout + out]);
-        if (!(a.flags & FINC_FLAG_NO_MASK) && ab == ca * KW + cbn && i >= o) v = 0.f;
-        if (a.flags & FINC_FLAG_ACCUMULATE) v += a.dw[out];
-        a.dw[out] = v;
+#pragma unroll 8
+        for (int xx = 0; xx < a.X; ++xx) v += __ldcg(pp + (long)xx * xstride);
+        finish(l, v);
     }
     if (threadIdx.x == 0) a.counters[g * a.Z + zz] = 0u;  // leave the ticket clean
 }
 
-template <int OBW, int KH, int KW>
-int launch_inst(const WgArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
-    auto kern = wgrad_kernel<OBW, KH, KW>;
+template <int OB, int WT, int KH, int KW>
+int launch_inst(const WgArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    auto kern = wgrad_kernel<OB, WT, KH, KW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    kern<<<grid, kWarps * 32, smem, st>>>(a);
+    kern<<<grid, threads, smem, st>>>(a);
     return (int)cudaGetLastError();
 }
 
-// output-channel block per warp job; 0 = shape not covered by the tiled kernel
-int pick_obw(int C, int kH, int kW) {
-    if (kH == 3 && kW == 3) {
-        if (C <= 4) return C;
-        if (C % 12 == 0) return 12;
-        if (C % 6 == 0) return 6;
-        if (C % 4 == 0) return 4;
-        if (C % 3 == 0) return 3;
-        return 4;
+template <int OB, int WT>
+int dispatch_k(int kH, const WgArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    if (kH == 3) return launch_inst<OB, WT, 3, 3>(a, grid, threads, smem, st);
+    if constexpr (OB <= 2) {
+        if (kH == 5) return launch_inst<OB, WT, 5, 5>(a, grid, threads, smem, st);
     }
-    if (kH == 5 && kW == 5) {
-        if (C <= 4) return C;
-        if (C % 4 == 0) return 4;
-        if (C % 3 == 0) return 3;
-        return 4;
-    }
-    return 0;
+    return FINC_E_UNSUPPORTED;
 }
 
+template <int OB>
+int dispatch_wt(int WT, int kH, const WgArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    if (WT == 4) return dispatch_k<OB, 4>(kH, a, grid, threads, smem, st);
+    return dispatch_k<OB, 2>(kH, a, grid, threads, smem, st);
+}
+
+unsigned magic(unsigned d) { return d <= 1 ? 0u : (unsigned)(((1ull << 32) + d - 1) / d); }
+
 struct Plan {
-    int obw, nobw, jpc, rsw, Z, X, ipc, nchunks;
+    int OB, WT, nob, nstrip, RR, rpr, slots, SP, ncombo, cpc, Z, X, CH, S, nchunks, threads;
+    size_t smem;
 };
 
 bool make_plan(const Shape& s, Plan* p) {
-    p->obw = pick_obw(s.C, s.kH, s.kW);
-    if (!p->obw) return false;
+    if (!(s.kH == s.kW && (s.kH == 3 || s.kH == 5))) return false;
+    if (s.W % 4 == 0) p->WT = 4;
+    else if (s.W % 2 == 0 && s.kW - 1 <= 2) p->WT = 2;  // vector halo needs HALO <= WT
+    else return false;
     const long tile_bytes = (long)s.C * s.H * s.W * 4;
-    if (tile_bytes > 32 * 1024) return false;
-    p->nobw = (s.C + p->obw - 1) / p->obw;
-    const int njobs = s.C * p->nobw;
-    p->jpc = njobs < kWarps ? njobs : kWarps;
-    p->rsw = kWarps / p->jpc;
-    p->Z = (njobs + p->jpc - 1) / p->jpc;
-    if ((long)s.G * p->Z * 4 > kCounterBytes) return false;
-    int ipc = (int)(16 * 1024 / tile_bytes);
-    if (ipc < 1) ipc = 1;
-    if (ipc > 16) ipc = 16;
-    if (ipc > s.B) ipc = s.B;
+    if (tile_bytes > 24 * 1024) return false;
     const int sms = sm_count_cached();
-    int xmax = sms / (s.G * p->Z);
-    if (xmax < 1) xmax = 1;
-    // keep at least ~2 chunks per CTA when the batch allows it
-    while (ipc > 1 && (s.B + ipc - 1) / ipc < 2 * xmax) ipc >>= 1;
-    p->ipc = ipc;
-    p->nchunks = (s.B + ipc - 1) / ipc;
-    p->X = xmax < p->nchunks ? xmax : p->nchunks;
+    p->nstrip = s.W / p->WT;
+    const int max_ob = s.kH == 3 ? 6 : 2;
+    const size_t budget = max_optin_smem_cached() > 8192 ? max_optin_smem_cached() - 4096 : 0;
+    Plan best{};
+    bool have = false;
+    // candidates from the most FMA-efficient output block down; keep the first that gives each
+    // SM a few hundred lanes, else the one with the most lanes
+    long best_lanes = -1;
+    for (int ob : {6, 4, 3, 2, 1}) {
+        if (ob > max_ob || ob > s.C) continue;
+        if (s.C % ob != 0 && !(ob == 4 && s.C > 6) && ob != 1) continue;
+        Plan q = *p;
+        q.OB = ob;
+        q.nob = (s.C + ob - 1) / ob;
+        q.ncombo = s.C * q.nob;
+        // CTAs per group first assuming Z = 1
+        int xmax = sms / s.G;
+        if (xmax < 1) xmax = 1;
+        int CH = (s.B + xmax - 1) / xmax;  // one chunk per CTA when the batch is small
+        const int ch_mem = (int)((budget / 2) / (2 * tile_bytes));  // two tensors, leave half for stages
+        if (CH > ch_mem) CH = ch_mem;
+        if (CH > 16) CH = 16;
+        if (CH < 1) CH = 1;
+        const int maxthr = max_consumer_warps(ob, s.kH) * 32;
+        // row ranges: as many as useful (>= 2 rows each) while the combos still fit one CTA
+        int RR = 1;
+        for (int r : {4, 2, 1}) {
+            if ((s.H + r - 1) / r < 2 && r > 1) continue;
+            RR = r;
+            const int slots = CH * q.nstrip * r;
+            const int SP = slots <= 32 ? (slots <= 1 ? 1 : 1 << (32 - __builtin_clz(slots - 1))) : ((slots + 31) / 32) * 32;
+            if ((long)SP * q.ncombo <= maxthr) break;
+        }
+        for (;;) {
+            q.RR = RR;
+            q.slots = CH * q.nstrip * RR;
+            q.SP = q.slots <= 32 ? (q.slots <= 1 ? 1 : 1 << (32 - __builtin_clz(q.slots - 1))) : ((q.slots + 31) / 32) * 32;
+            if (q.SP <= maxthr || CH == 1) break;
+            --CH;
+        }
+        if (q.SP > maxthr) continue;
+        q.CH = CH;
+        q.rpr = (s.H + RR - 1) / RR;
+        q.cpc = maxthr / q.SP;
+        if (q.cpc > q.ncombo) q.cpc = q.ncombo;
+        q.Z = (q.ncombo + q.cpc - 1) / q.cpc;
+        if ((long)s.G * q.Z * 4 > kCounterBytes) continue;
+        q.nchunks = (s.B + CH - 1) / CH;
+        int x = sms / (s.G * q.Z);
+        if (x < 1) x = 1;
+        q.X = x < q.nchunks ? x : q.nchunks;
+        const int cpcta = (q.nchunks + q.X - 1) / q.X;
+        q.S = cpcta < 3 ? cpcta : 3;
+        q.threads = ((q.cpc * q.SP + 31) / 32 + 1) * 32;
+        const int nacc = ob * s.kH * s.kW;
+        const int nseg = (q.threads - 32) / (q.SP < 32 ? q.SP : 32);
+        for (;;) {
+            q.smem = (size_t)kFrontPad * 4 + (size_t)q.S * 2 * CH * tile_bytes + 32 + (size_t)(nseg * nacc + 2) * 4 +
+                     2 * q.S * 8 + 64;
+            if (q.smem <= budget || q.S == 1) break;
+            --q.S;
+        }
+        if (q.smem > budget) continue;
+        const long lanes = (long)q.cpc * q.slots;  // busy lanes per CTA
+        if (lanes >= 256) { best = q; have = true; break; }
+        if (lanes > best_lanes) { best = q; best_lanes = lanes; have = true; }
+    }
+    if (!have) return false;
+    *p = best;
     return true;
 }
 
 }  // namespace
 
+static size_t partial_floats(const Shape& s, const Plan& p) {
+    return (size_t)p.X * s.G * p.Z * p.cpc * p.OB * s.kH * s.kW;
+}
+
 size_t wgrad_workspace_floats(const Shape& s) {
-    Plan p;
-    const long nout = (long)s.G * s.C * s.C * s.kH * s.kW;
+    Plan p{};
     if (!make_plan(s, &p)) return kCounterBytes / 4;
-    return kCounterBytes / 4 + (size_t)p.X * nout;
+    return kCounterBytes / 4 + partial_floats(s, p);
 }
 
 int launch_wgrad_fast(const float* dz, const float* x, float* dw, float* workspace, size_t ws_floats, const Shape& s,
                       unsigned flags, cudaStream_t st, bool* handled) {
     *handled = false;
-    Plan p;
+    Plan p{};
     if (!make_plan(s, &p)) return 0;
-    const long nout = (long)s.G * s.C * s.C * s.kH * s.kW;
-    if (ws_floats < kCounterBytes / 4 + (size_t)p.X * nout) return FINC_E_WORKSPACE;
+    if (ws_floats < kCounterBytes / 4 + partial_floats(s, p)) return FINC_E_WORKSPACE;
     WgArgs a{};
     a.dz = dz; a.x = x; a.dw = dw; a.s = s; a.flags = flags;
     a.counters = reinterpret_cast<unsigned*>(workspace);
     a.partial = workspace + kCounterBytes / 4;
-    a.ipc = p.ipc; a.nobw = p.nobw; a.jpc = p.jpc; a.rsw = p.rsw; a.X = p.X; a.Z = p.Z; a.nchunks = p.nchunks;
+    a.CH = p.CH; a.S = p.S; a.nob = p.nob; a.nstrip = p.nstrip; a.RR = p.RR; a.rpr = p.rpr;
+    a.slots = p.slots; a.SP = p.SP; a.ncombo = p.ncombo; a.cpc = p.cpc; a.X = p.X; a.Z = p.Z; a.nchunks = p.nchunks;
+    a.m_nstrip = magic(p.nstrip); a.m_rr = magic(p.RR);
     a.tile_floats = s.C * s.H * s.W;
-    a.tile_stride = (a.tile_floats + 3) & ~3;
     a.bulk = (a.tile_floats % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
              ((reinterpret_cast<uintptr_t>(dz) & 15) == 0);
-    const int nacc = p.obw * s.kH * s.kW;
-    const size_t smem = (size_t)4 * a.ipc * a.tile_stride * 4 + (size_t)(kWarps * nacc + 1) * 4 + 32;
-    if (smem > max_optin_smem_cached()) return 0;
-    if (a.X > 1) {
+    if (a.X > 1 && !(flags & FINC_FLAG_WORKSPACE_CLEAN)) {
         cudaError_t e = cudaMemsetAsync(a.counters, 0, (size_t)s.G * a.Z * 4, st);
         if (e != cudaSuccess) return (int)e;
     }
     dim3 grid(a.X, s.G, a.Z);
-    *handled = true;
-    if (s.kH == 3) {
-        switch (p.obw) {
-            case 1: return launch_inst<1, 3, 3>(a, grid, smem, st);
-            case 2: return launch_inst<2, 3, 3>(a, grid, smem, st);
-            case 3: return launch_inst<3, 3, 3>(a, grid, smem, st);
-            case 4: return launch_inst<4, 3, 3>(a, grid, smem, st);
-            case 6: return launch_inst<6, 3, 3>(a, grid, smem, st);
-            case 12: return launch_inst<12, 3, 3>(a, grid, smem, st);
-        }
-    } else {
-        switch (p.obw) {
-            case 1: return launch_inst<1, 5, 5>(a, grid, smem, st);
-            case 2: return launch_inst<2, 5, 5>(a, grid, smem, st);
-            case 3: return launch_inst<3, 5, 5>(a, grid, smem, st);
-            case 4: return launch_inst<4, 5, 5>(a, grid, smem, st);
-        }
+    int rc;
+    switch (p.OB) {
+        case 1: rc = dispatch_wt<1>(p.WT, s.kH, a, grid, p.threads, p.smem, st); break;
+        case 2: rc = dispatch_wt<2>(p.WT, s.kH, a, grid, p.threads, p.smem, st); break;
+        case 3: rc = dispatch_wt<3>(p.WT, s.kH, a, grid, p.threads, p.smem, st); break;
+        case 4: rc = dispatch_wt<4>(p.WT, s.kH, a, grid, p.threads, p.smem, st); break;
+        default: rc = dispatch_wt<6>(p.WT, s.kH, a, grid, p.threads, p.smem, st); break;
     }
-    *handled = false;
-    return 0;
+    if (rc == FINC_E_UNSUPPORTED) return 0;
+    *handled = true;
+    return rc;
 }
 
 }  // namespace finc

@@ -161,7 +161,7 @@ class HotPathRunner:
         for lv in stack.levels:
             ws = max(ws, _native.backward_weight_workspace_bytes(batch, 4, lv.cq, lv.height, lv.width,
                                                                  *lv.kernel_size))
-        self.workspace = torch.empty(ws, dtype=torch.uint8, device=self.device)
+        self.workspace = _native.new_workspace(ws, self.device)
         self.slots = [_Slot(stack, batch, self.device, host_io) for _ in range(slots)]
         self.graphs = [None] * slots
         self.launches_per_step = None

@@ -49,6 +49,7 @@ extern "C" {
 #define FINC_FLAG_NO_MASK 2u      /* backward_weight: do NOT apply the FInC gradient mask */
 #define FINC_FLAG_ACCUMULATE 4u   /* backward_weight: dw += result instead of dw = result */
 #define FINC_FLAG_GENERIC_TILED 16u /* inverse: skip the shape-specialised kernel, use the generic tiled one (testing) */
+#define FINC_FLAG_WORKSPACE_CLEAN 32u /* backward_weight: the first 4 KiB of `workspace` are zero (as every call leaves them) */
 #define FINC_FLAG_LOGDET_ACCUMULATE 8u /* forward: logdet[n] += ... (FlowSequential's `logdet += layer_logdet`) */
 
 /* error codes (negative); positive return values are cudaError_t */
@@ -87,7 +88,10 @@ int finc_backward_input_f32(const float* dz, const float* w, float* dx,
  * Replaces cuDNN wgrad + PaddedConv2d.reset_gradients / clear_grad
  * (layers/conv.py:81-99, train/experiment.py:16-18,250).  `dw` may point into a flat
  * gradient bucket.  `workspace` must hold finc_backward_weight_workspace_bytes(...)
- * bytes of device memory (contents irrelevant on entry). */
+ * bytes of device memory.  Its first 4 KiB are ticket counters: they are cleared by the call
+ * (one memset node) unless FINC_FLAG_WORKSPACE_CLEAN promises they are already zero; every
+ * successful call leaves them zero, so a workspace zeroed once can be reused with the flag.
+ * Calls sharing a workspace must be stream-ordered. */
 size_t finc_backward_weight_workspace_bytes(int B, int G, int C, int H, int W, int kH, int kW);
 int finc_backward_weight_f32(const float* dz, const float* x, float* dw,
                              void* workspace, size_t workspace_bytes,

@@ -29,7 +29,7 @@ for shp in args.shapes.split(","):
     dz = torch.randn_like(x)
     y = torch.empty_like(x)
     dw = torch.empty_like(w)
-    ws = torch.empty(_native.backward_weight_workspace_bytes(B, 4, CT // 4, H, W, k, k), dtype=torch.uint8, device=dev)
+    ws = _native.new_workspace(_native.backward_weight_workspace_bytes(B, 4, CT // 4, H, W, k, k), dev)
     fns = {
         "forward": lambda: _native.forward(x, w, out=y, want_logdet=False),
         "backward_input": lambda: _native.backward_input(dz, w, out=y),

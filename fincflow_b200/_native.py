@@ -30,7 +30,7 @@ SYMBOLS = (
     "finc_abi_version", "finc_error_string", "finc_set_device", "finc_sm_count",
     "finc_forward_f32", "finc_backward_input_f32", "finc_backward_weight_workspace_bytes",
     "finc_backward_weight_f32", "finc_inverse_f32", "finc_apply_grad_mask_f32", "finc_logdet_f32",
-    "finc_gaussian_logp_f32",
+    "finc_gaussian_logp_f32", "finc_debug_timestamps",
 )
 
 _lib = None

@@ -4,7 +4,23 @@
 // GPU kernels otherwise.  There is no CPU path.
 #include "finc_common.cuh"
 
+#include <cstdlib>
+
 namespace finc {
+
+__device__ unsigned long long g_finc_dbg[kDbgCtas * kDbgSlots];
+
+unsigned long long* debug_ts_buffer() {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("FINC_DEBUG_TS");
+        enabled = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (!enabled) return nullptr;
+    void* p = nullptr;
+    if (cudaGetSymbolAddress(&p, g_finc_dbg) != cudaSuccess) return nullptr;
+    return static_cast<unsigned long long*>(p);
+}
 
 static int g_sm_count[64];
 static size_t g_smem_optin[64];
@@ -168,6 +184,15 @@ int finc_gaussian_logp_f32(const float* z, const float* logdet, float* logp, flo
     if (B == 0) return FINC_OK;
     if (!z || !logp) return FINC_E_BADARG;
     return launch_gaussian_logp(z, logdet, logp, dz, dz_scale, B, D, (cudaStream_t)stream);
+}
+
+/* debug only (FINC_DEBUG_TS=1): copy the per-CTA timestamp marks of the last launch (synchronises) */
+int finc_debug_timestamps(unsigned long long* host_out, int n) {
+    if (!host_out || n <= 0) return FINC_E_BADARG;
+    if (n > kDbgCtas * kDbgSlots) n = kDbgCtas * kDbgSlots;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaMemcpyFromSymbol(host_out, g_finc_dbg, sizeof(unsigned long long) * n);
 }
 
 }  // extern "C"

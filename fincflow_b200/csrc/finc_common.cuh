@@ -84,6 +84,61 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+
+// Cooperative gather of `n` contiguous weights starting at `src` with all loads of a batch in
+// flight before the first scatter: f(e, value) places element e.  (The dependent
+// load -> index math -> store loop costs one global round trip per iteration.)
+template <typename F>
+__device__ __forceinline__ void stage_weights(const float* __restrict__ src, int n, F&& f) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const int n4 = n >> 2;
+        const float4* src4 = reinterpret_cast<const float4*>(src);
+        for (int base = 0; base < n4; base += 4 * nthr) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e4 = base + u * nthr + tid;
+                if (e4 < n4) v[u] = __ldg(src4 + e4);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e4 = base + u * nthr + tid;
+                if (e4 < n4) { f(4 * e4, v[u].x); f(4 * e4 + 1, v[u].y); f(4 * e4 + 2, v[u].z); f(4 * e4 + 3, v[u].w); }
+            }
+        }
+        for (int e = (n4 << 2) + tid; e < n; e += nthr) f(e, __ldg(src + e));
+    } else {
+        for (int base = 0; base < n; base += 8 * nthr) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = base + u * nthr + tid;
+                if (e < n) v[u] = __ldg(src + e);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = base + u * nthr + tid;
+                if (e < n) f(e, v[u]);
+            }
+        }
+    }
+}
+
+// ---- debug timestamps (FINC_DEBUG_TS=1): per-CTA %globaltimer marks, read back with
+// finc_debug_timestamps(); never enabled in normal operation --------------------------------
+constexpr int kDbgSlots = 8;
+constexpr int kDbgCtas = 1024;
+__device__ __forceinline__ void dbg_mark(unsigned long long* buf, int slot) {
+    if (buf) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        if (cta < kDbgCtas) buf[cta * kDbgSlots + slot] = t;
+    }
+}
+unsigned long long* debug_ts_buffer();  // device pointer, or nullptr when disabled
+
 __device__ __forceinline__ bool is_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---------------------------------------------------------------------------------------

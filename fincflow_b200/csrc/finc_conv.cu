@@ -52,7 +52,7 @@ int launch_conv_fast(const float* x, const float* w, float* y, float* logdet, bo
     if (tile_floats_l * 4 > 48 * 1024) return 0;
     ConvArgs a{};
     a.x = x; a.w = w; a.y = y; a.logdet = transpose ? nullptr : logdet; a.logdet_acc = logdet_acc ? 1 : 0;
-    a.s = s; a.transpose = transpose ? 1 : 0;
+    a.s = s; a.transpose = transpose ? 1 : 0; a.dbg = debug_ts_buffer();
     a.tile_floats = (int)tile_floats_l;
     a.bulk = (a.tile_floats % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     int WT = 1;

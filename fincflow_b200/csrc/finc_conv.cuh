@@ -52,6 +52,7 @@ struct ConvArgs {
     int wk_floats;    // weight floats in smem (all groups or one)
     int nstrip;       // W / WT
     unsigned m_nstrip, m_h, m_nob;  // magic multipliers for division by nstrip, H, nob
+    unsigned long long* dbg;  // debug timestamps (nullptr = off)
     int nblk;         // image blocks = ceil(B / CH)
     long n_chunks;    // nblk * G (or nblk when gsplit)
 };
@@ -234,6 +235,7 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kern
                      a.x + ((long)(n0 + t) * s.G + g) * a.tile_floats, (uint32_t)(a.tile_floats * 4), &full[st]);
     };
 
+    if (threadIdx.x == 0) dbg_mark(a.dbg, 0);
     // ---- start-up: barriers and first loads, then the weight staging (overlaps the loads) ----
     if (a.bulk && is_producer && lane == 0) {
         for (int st = 0; st < a.S; ++st) {
@@ -253,11 +255,10 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kern
         const int per_g = C * C * kk;
         const int ng = a.gsplit ? 1 : s.G;
         if (threadIdx.x < kFrontPad) wk[wk_pad + threadIdx.x] = 0.f;
-        for (int e = threadIdx.x; e < ng * per_g; e += blockDim.x) {
+        const float* wsrc = a.w + (a.gsplit ? (long)g_fixed * per_g : 0);
+        stage_weights(wsrc, ng * per_g, [&](int e, float v) {
             const int gl = e / per_g;
-            const int g = a.gsplit ? g_fixed : gl;
             int r = e - gl * per_g;
-            const float v = __ldg(a.w + (long)g * per_g + r);
             const int b = r % KW;
             r /= KW;
             const int aa = r % KH;
@@ -267,8 +268,9 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kern
             if (!a.transpose) { cin = i; cout = o; ap = aa; bp = b; }
             else { cin = o; cout = i; ap = KH - 1 - aa; bp = KW - 1 - b; }
             wk[((((gl * C + cin) * KH + ap) * KW + bp) * a.nob + cout / OB) * OBP + cout % OB] = v;
-        }
+        });
         __syncthreads();
+        if (threadIdx.x == 0) dbg_mark(a.dbg, 1);
     }
 
     if (is_producer) {
@@ -307,6 +309,7 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kern
         float* buf = bufs + (size_t)st * stage_floats;
         if (a.bulk) {
             mbar_wait(&full[st], (uint32_t)((k / a.S) & 1));
+            if (threadIdx.x == 0 && k == 0) dbg_mark(a.dbg, 2);
         } else {
             // unaligned tensors: cooperative copy by the consumer threads
             asm volatile("bar.sync 1, %0;" ::"r"(nthreads_c) : "memory");  // previous chunk fully consumed
@@ -338,6 +341,7 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kern
             if (right) conv_sub<CT, OB, WT, KH, KW, true>(xt, zrow, wg, yt, C, H, W, HW, h, w0, r0, ob, nob);
             else conv_sub<CT, OB, WT, KH, KW, false>(xt, zrow, wg, yt, C, H, W, HW, h, w0, r0, ob, nob);
         }
+        if (threadIdx.x == 0) dbg_mark(a.dbg, 3);
         if (a.bulk) {
             __syncwarp();
             if (lane == 0) {  // release the stage: one arrival per consumer warp

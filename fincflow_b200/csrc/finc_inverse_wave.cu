@@ -25,7 +25,7 @@ int launch_inverse_wave(const float* z, const float* w, float* x, const Shape& s
     const long tile_floats_l = (long)C * s.H * s.W;
     if (tile_floats_l * 4 > 64 * 1024) return 0;
     WaveArgs a{};
-    a.z = z; a.w = w; a.x = x; a.s = s;
+    a.z = z; a.w = w; a.x = x; a.s = s; a.dbg = debug_ts_buffer();
     a.tile_floats = (int)tile_floats_l;
     a.tile_stride = (a.tile_floats + 3) & ~3;
     const int CPP = C <= 2 ? C : ((C + 3) / 4) * 4;

@@ -20,12 +20,14 @@
 //   * kernel size and channel count are template parameters: tap offsets, bounds and the
 //     triangular solve are fully unrolled; no integer division in the step loop.
 #pragma once
+#include <type_traits>
+
 #include "finc_common.cuh"
 
 namespace finc {
 namespace wave {
 
-constexpr int kMaxWarps = 16;
+constexpr int kMaxWarps = 12;  // 384 threads: up to 170 registers per lane (weights + both streams)
 
 struct WaveArgs {
     const float* z;
@@ -39,6 +41,7 @@ struct WaveArgs {
     int tile_floats;
     int tile_stride;
     int wk_floats;
+    unsigned long long* dbg;
     long n_items;
 };
 
@@ -57,8 +60,6 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
     constexpr int CPP = Pad4<C>::value;
     constexpr int TS = Pad4<C>::tap_stride;
     constexpr int NT = KH * KW - 1;          // non-corner taps
-    constexpr int NTL = (NT + P - 1) / P;    // taps per lane
-    constexpr bool WREG = (NTL * C * C <= 72);  // tap weights in registers
     constexpr bool CREG = (C <= 6);             // corner weights in registers
     constexpr int CB = 32 / P;                  // columns per block
 
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
                      (uint32_t)(a.tile_floats * 4), &bars[st]);
     };
 
+    if (threadIdx.x == 0) dbg_mark(a.dbg, 0);
     const int n_pre = a.S == 3 ? 2 : a.S;
     if (a.bulk && lane == 0) {
         for (int st = 0; st < a.S; ++st) mbar_init(&bars[st], 1);
@@ -103,7 +105,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
         // (padding lanes o >= C of a row are never read into a stored result)
         constexpr int per_g = C * C * KH * KW;
         const int ng = a.gsplit ? 1 : s.G;
-        for (int e = threadIdx.x; e < ng * per_g; e += blockDim.x) {
+        const float* wsrc = a.w + (a.gsplit ? (long)g_fixed * per_g : 0);
+        stage_weights(wsrc, ng * per_g, [&](int e, float v) {
             const int gl = e / per_g;
             const int g = a.gsplit ? g_fixed : gl;
             int r = e - gl * per_g;
@@ -115,22 +118,51 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
             const int ord = order_of(s.orders, g);
             const int kh = (ord & 2) ? aa : KH - 1 - aa;
             const int kw = (ord & 1) ? b : KW - 1 - b;
-            wk[((gl * KH + kh) * KW + kw) * TS + i * CPP + o] = __ldg(a.w + (long)g * per_g + (e - gl * per_g));
-        }
+            wk[((gl * KH + kh) * KW + kw) * TS + i * CPP + o] = v;
+        });
         __syncthreads();
+        if (threadIdx.x == 0) dbg_mark(a.dbg, 1);
     }
 
     const int jj = lane / P;       // column slot
     const int p = lane - jj * P;   // part
     const int ncb = (W + CB - 1) / CB;
 
-    // taps owned by this lane (sweep coordinates); q enumerates (kh,kw) != (0,0) row-major
-    int tkh[NTL], tkw[NTL];
+    // Taps in sweep coordinates (kh, kw) != (0,0).  NEAR taps (0,1) and (1,0) read pixels of the
+    // previous anti-diagonal: they are the critical path.  FAR taps (kh + kw >= 2) read pixels
+    // that are at least two diagonals old, so the far part of the NEXT pixel is computed in the
+    // shadow of the current pixel's near part / shuffle reduction / triangular solve.
+    // With P <= 2 parts per pixel the two streams are split (PIPE); with more parts the near
+    // taps would sit on 2 of the P lanes only, so all taps stay in one balanced phase.
+    constexpr bool PIPE = P <= 2;
+    constexpr int SC = C;                                  // input channels per slot (a slot is a tap)
+    constexpr int NNEAR = PIPE ? 2 : NT;                   // slots on the critical path
+    constexpr int NFAR = PIPE ? NT - 2 : 0;                // slots computed one step ahead
+    constexpr int NNL = (NNEAR + P - 1) / P;               // per lane
+    constexpr int NFL = (NFAR + P - 1) / P;
+    constexpr int NFLA = NFL > 0 ? NFL : 1;
+    constexpr bool WN_REG = (NNL * SC * C <= 40);
+    constexpr bool WF_REG = WN_REG && ((NNL + NFL) * SC * C <= 48);
+    int nkh[NNL], nkw[NNL], nch[NNL], fkh[NFLA], fkw[NFLA], fch[NFLA];
 #pragma unroll
-    for (int m = 0; m < NTL; ++m) {
-        const int q = m * P + p;
-        tkh[m] = (q < NT) ? (q + 1) / KW : KH + H;  // invalid taps never pass the bounds test
-        tkw[m] = (q < NT) ? (q + 1) % KW : 0;
+    for (int m = 0; m < NNL; ++m) {
+        const int e = m * P + p;
+        nch[m] = 0;
+        if constexpr (PIPE) {                     // 0 -> (0,1), 1 -> (1,0)
+            nkh[m] = e < NNEAR ? (e == 1 ? 1 : 0) : KH + H;   // slots past the end never pass the bounds test
+            nkw[m] = (e < NNEAR && e == 0) ? 1 : 0;
+        } else {                                  // all taps, row-major without (0,0)
+            nkh[m] = e < NNEAR ? (e + 1) / KW : KH + H;
+            nkw[m] = e < NNEAR ? (e + 1) % KW : 0;
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < NFL; ++m) {
+        const int e = m * P + p;
+        fch[m] = 0;
+        const int q = e < KW - 2 ? e + 1 : e + 2;  // skip q = 0 (0,1) and q = KW-1 (1,0)
+        fkh[m] = (e < NFAR) ? (q + 1) / KW : KH + H;
+        fkw[m] = (e < NFAR) ? (q + 1) % KW : 0;
     }
 
     long k = 0;
@@ -141,6 +173,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
         float* buf = bufs + st * stage_floats;
         if (a.bulk) {
             mbar_wait(&bars[st], (uint32_t)((k / a.S) & 1));
+            if (threadIdx.x == 0 && k == 0) dbg_mark(a.dbg, 2);
         } else {
             for (int t = 0; t < nt; ++t) {
                 const float* src = a.z + ((long)(n0 + t) * s.G + g) * a.tile_floats;
@@ -152,21 +185,35 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
         const bool bot = ord & 2, right = ord & 1;
         const float* wg = wk + (size_t)(a.gsplit ? 0 : g) * KH * KW * TS;
 
-        // per-item register weights
-        float wr[WREG ? NTL : 1][WREG ? C : 1][WREG ? C : 1];
+        // per-item slot tables: shared-memory offset, weight row, register weights
+        int noff[NNL], foff[NFLA];
+        const float* nwp[NNL];
+        const float* fwp[NFLA];
+        float wn[WN_REG ? NNL : 1][WN_REG ? SC : 1][WN_REG ? C : 1];
+        float wf[WF_REG ? NFLA : 1][WF_REG ? SC : 1][WF_REG ? C : 1];
         float wc[CREG ? C : 1][CREG ? C : 1];
-        int toff[NTL];
-        const float* wp[NTL];
 #pragma unroll
-        for (int m = 0; m < NTL; ++m) {
-            toff[m] = (bot ? tkh[m] : -tkh[m]) * W + (right ? tkw[m] : -tkw[m]);
-            const int q = m * P + p;
-            wp[m] = wg + (size_t)((q < NT ? tkh[m] : 0) * KW + tkw[m]) * TS;
-            if constexpr (WREG) {
+        for (int m = 0; m < NNL; ++m) {
+            const bool real = m * P + p < NNEAR;
+            noff[m] = (bot ? nkh[m] : -nkh[m]) * W + (right ? nkw[m] : -nkw[m]) + nch[m] * HW;
+            nwp[m] = wg + (size_t)((real ? nkh[m] : 0) * KW + nkw[m]) * TS + nch[m] * CPP;
+            if constexpr (WN_REG) {
 #pragma unroll
-                for (int i = 0; i < C; ++i)
+                for (int i = 0; i < SC; ++i)
 #pragma unroll
-                    for (int o = 0; o < C; ++o) wr[m][i][o] = (q < NT) ? wp[m][i * CPP + o] : 0.f;
+                    for (int o = 0; o < C; ++o) wn[m][i][o] = real ? nwp[m][i * CPP + o] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < NFL; ++m) {
+            const bool real = m * P + p < NFAR;
+            foff[m] = (bot ? fkh[m] : -fkh[m]) * W + (right ? fkw[m] : -fkw[m]) + fch[m] * HW;
+            fwp[m] = wg + (size_t)((real ? fkh[m] : 0) * KW + fkw[m]) * TS + fch[m] * CPP;
+            if constexpr (WF_REG) {
+#pragma unroll
+                for (int i = 0; i < SC; ++i)
+#pragma unroll
+                    for (int o = 0; o < C; ++o) wf[m][i][o] = real ? fwp[m][i * CPP + o] : 0.f;
             }
         }
         if constexpr (CREG) {
@@ -176,6 +223,26 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
                 for (int o = 0; o < C; ++o) wc[i][o] = wg[i * CPP + o];
         }
 
+        // acc[o] += xv * w[i][o] (xv already negated) for channel i of a slot
+        auto fma_row = [&](float (&acc)[C], float xv, const float* wrow, const float* wreg) {
+            if (wreg != nullptr) {
+#pragma unroll
+                for (int o = 0; o < C; ++o) acc[o] = fmaf(xv, wreg[o], acc[o]);
+            } else if constexpr (CPP % 4 == 0) {
+#pragma unroll
+                for (int v = 0; v < CPP / 4; ++v) {
+                    const float4 f = *reinterpret_cast<const float4*>(wrow + 4 * v);
+                    if (4 * v + 0 < C) acc[4 * v + 0] = fmaf(xv, f.x, acc[4 * v + 0]);
+                    if (4 * v + 1 < C) acc[4 * v + 1] = fmaf(xv, f.y, acc[4 * v + 1]);
+                    if (4 * v + 2 < C) acc[4 * v + 2] = fmaf(xv, f.z, acc[4 * v + 2]);
+                    if (4 * v + 3 < C) acc[4 * v + 3] = fmaf(xv, f.w, acc[4 * v + 3]);
+                }
+            } else {
+#pragma unroll
+                for (int o = 0; o < C; ++o) acc[o] = fmaf(xv, wrow[o], acc[o]);
+            }
+        };
+
         const int R = nt * H;  // stacked rows
         for (int cb = 0; cb < ncb; ++cb) {
             const int ws = cb * CB + jj;  // sweep column
@@ -183,78 +250,83 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
             const bool col_on = jj < nc;
             const int wst = right ? W - 1 - ws : ws;
             const int nsteps = R + nc - 1;
-            int hs = -jj;  // sweep row inside the current tile (valid once r >= 0)
-            int r = -jj;   // stacked row
-            float* xt = buf;
-            for (int step = 0; step < nsteps; ++step) {
-                const bool act = col_on && r >= 0 && r < R;
+            // current pixel (finished this step) and next pixel (far part prefetched this step)
+            bool act_c = false;
+            int hs_c = 0;
+            float* base_c = buf;
+            float accf[C];
+#pragma unroll
+            for (int o = 0; o < C; ++o) accf[o] = 0.f;
+            int hn = 0;        // row of the next pixel inside its tile
+            float* xn = buf;   // tile of the next pixel
+            for (int step = -1; step < nsteps; ++step) {
+                // (1) loads of the current pixel's near slots: the only ones that wait for the
+                //     previous diagonal
+                float xa[NNL][SC];
+#pragma unroll
+                for (int m = 0; m < NNL; ++m) {
+                    const bool valid = act_c && hs_c >= nkh[m] && ws >= nkw[m];
+#pragma unroll
+                    for (int i = 0; i < SC; ++i) xa[m][i] = valid ? -base_c[noff[m] + i * HW] : 0.f;
+                }
+                // (2) loads for the far part of the NEXT pixel (two or more diagonals old)
+                const int rn = step + 1 - jj;
+                const bool act_n = col_on && rn >= 0 && rn < R;
+                float* base_n = xn + (bot ? H - 1 - hn : hn) * W + wst;
+                float accn[C];
+#pragma unroll
+                for (int o = 0; o < C; ++o) accn[o] = (act_n && p == 0) ? base_n[o * HW] : 0.f;  // z enters once
+                float xb[NFLA][SC];
+#pragma unroll
+                for (int m = 0; m < NFL; ++m) {
+                    const bool valid = act_n && hn >= fkh[m] && ws >= fkw[m];
+#pragma unroll
+                    for (int i = 0; i < SC; ++i) xb[m][i] = valid ? -base_n[foff[m] + i * HW] : 0.f;
+                }
+                // (3) near FMAs, then the P partial sums of the pixel start their shuffle reduction
                 float acc[C];
 #pragma unroll
-                for (int o = 0; o < C; ++o) acc[o] = 0.f;
-                int pix = 0;
-                if (act) {
-                    const int h = bot ? H - 1 - hs : hs;
-                    pix = h * W + wst;
-                    if (p == 0) {  // z enters the sum once; read before the shuffle barrier, written after it
+                for (int o = 0; o < C; ++o) acc[o] = accf[o];
 #pragma unroll
-                        for (int o = 0; o < C; ++o) acc[o] = xt[o * HW + pix];
-                    }
+                for (int m = 0; m < NNL; ++m)
 #pragma unroll
-                    for (int m = 0; m < NTL; ++m) {
-                        if (hs >= tkh[m] && ws >= tkw[m]) {
-                            const float* xs = xt + pix + toff[m];
-#pragma unroll(WREG ? C : (C <= 12 ? 2 : 1))
-                            for (int i = 0; i < C; ++i) {
-                                const float xv = -xs[i * HW];
-                                if constexpr (WREG) {
-#pragma unroll
-                                    for (int o = 0; o < C; ++o) acc[o] = fmaf(xv, wr[m][i][o], acc[o]);
-                                } else if constexpr (CPP % 4 == 0) {
-#pragma unroll
-                                    for (int v = 0; v < CPP / 4; ++v) {
-                                        const float4 f = *reinterpret_cast<const float4*>(wp[m] + i * CPP + 4 * v);
-                                        if (4 * v + 0 < C) acc[4 * v + 0] = fmaf(xv, f.x, acc[4 * v + 0]);
-                                        if (4 * v + 1 < C) acc[4 * v + 1] = fmaf(xv, f.y, acc[4 * v + 1]);
-                                        if (4 * v + 2 < C) acc[4 * v + 2] = fmaf(xv, f.z, acc[4 * v + 2]);
-                                        if (4 * v + 3 < C) acc[4 * v + 3] = fmaf(xv, f.w, acc[4 * v + 3]);
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int o = 0; o < C; ++o) acc[o] = fmaf(xv, wp[m][i * CPP + o], acc[o]);
-                                }
-                            }
-                        }
-                    }
-                }
-                // combine the P partial sums of the pixel (all lanes of a pixel share `act`)
-                if constexpr (P > 1) {  // (the shuffles also order the z reads above before the x writes below)
+                    for (int i = 0; i < SC; ++i)
+                        fma_row(acc, xa[m][i], nwp[m] + i * CPP, WN_REG ? &wn[WN_REG ? m : 0][WN_REG ? i : 0][0] : nullptr);
+                if constexpr (P > 1) {
 #pragma unroll
                     for (int off = 1; off < P; off <<= 1)
 #pragma unroll
                         for (int o = 0; o < C; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
                 }
-                if (act) {
-                    // corner tap: x[o] = acc[o] - sum_{i<o} W[o,i,corner] x[i]
+                // (4) far FMAs of the next pixel: independent work that fills the latency above
 #pragma unroll
-                    for (int i = 0; i < C - 1; ++i)
+                for (int m = 0; m < NFL; ++m)
 #pragma unroll
-                        for (int o = i + 1; o < C; ++o) {
-                            if constexpr (CREG) acc[o] = fmaf(-acc[i], wc[i][o], acc[o]);
-                            else acc[o] = fmaf(-acc[i], wg[i * CPP + o], acc[o]);
-                        }
+                    for (int i = 0; i < SC; ++i)
+                        fma_row(accn, xb[m][i], fwp[m] + i * CPP, WF_REG ? &wf[WF_REG ? m : 0][WF_REG ? i : 0][0] : nullptr);
+                // (5) corner tap: x[o] = acc[o] - sum_{i<o} W[o,i,corner] x[i]; one lane stores
 #pragma unroll
-                    for (int o = 0; o < C; ++o)
-                        if ((o % P) == p) xt[o * HW + pix] = acc[o];
-                    // advance inside the stack
-                    if (++hs == H) { hs = 0; xt += a.tile_stride; }
-                } else if (r < 0) {
-                    ++hs;
+                for (int i = 0; i < C - 1; ++i)
+#pragma unroll
+                    for (int o = i + 1; o < C; ++o) {
+                        if constexpr (CREG) acc[o] = fmaf(-acc[i], wc[i][o], acc[o]);
+                        else acc[o] = fmaf(-acc[i], wg[i * CPP + o], acc[o]);
+                    }
+                if (act_c && p == 0) {
+#pragma unroll
+                    for (int o = 0; o < C; ++o) base_c[o * HW] = acc[o];
                 }
-                ++r;
                 __syncwarp();
+#pragma unroll
+                for (int o = 0; o < C; ++o) accf[o] = accn[o];
+                act_c = act_n;
+                hs_c = hn;
+                base_c = base_n;
+                if (act_n && ++hn == H) { hn = 0; xn += a.tile_stride; }
             }
         }
 
+        if (threadIdx.x == 0 && k == 0) dbg_mark(a.dbg, 3);
         if (a.bulk) {
             fence_proxy_async_smem();
             __syncwarp();
@@ -282,6 +354,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
         }
     }
     if (a.bulk && lane == 0) bulk_wait_all();
+    if (threadIdx.x == 0) dbg_mark(a.dbg, 4);
 }
 
 template <int C, int KH, int KW, int P>

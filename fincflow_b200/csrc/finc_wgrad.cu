@@ -46,6 +46,7 @@ struct WgArgs {
     int slots, SP;             // slots per combo and its padded size (power of two <= 32, or multiple of 32)
     int ncombo, cpc;           // combos in total / per CTA
     int X, Z, nchunks;
+    unsigned long long* dbg;
     unsigned m_nstrip, m_rr;
 };
 
@@ -164,6 +165,7 @@ __global__ void __launch_bounds__((max_consumer_warps(OB, KH) + 1) * 32, 1) wgra
         }
     };
 
+    if (threadIdx.x == 0) dbg_mark(a.dbg, 0);
     if (a.bulk && is_producer && lane == 0) {
         for (int st = 0; st < a.S; ++st) {
             mbar_init(&full[st], 1);
@@ -221,6 +223,7 @@ __global__ void __launch_bounds__((max_consumer_warps(OB, KH) + 1) * 32, 1) wgra
             float* ds = xs + half;
             if (a.bulk) {
                 mbar_wait(&full[st], (uint32_t)((k / a.S) & 1));
+                if (threadIdx.x == 0 && k == 0) dbg_mark(a.dbg, 1);
             } else {
                 asm volatile("bar.sync 1, %0;" ::"r"(nthreads_c) : "memory");
                 for (int tt = 0; tt < nt; ++tt) {
@@ -244,21 +247,30 @@ __global__ void __launch_bounds__((max_consumer_warps(OB, KH) + 1) * 32, 1) wgra
             }
         }
 
+        if (threadIdx.x == 0) dbg_mark(a.dbg, 2);
         // ---- lanes of a combo -> one value per segment (segment = min(SP,32) consecutive lanes) ------
+        // level-major: the NACC shuffles of one level are independent and pipeline
         const int SPw = a.SP < 32 ? a.SP : 32;
         const int seg = threadIdx.x / SPw;
+        for (int off = 1; off < SPw; off <<= 1) {
 #pragma unroll
-        for (int o = 0; o < OB; ++o)
+            for (int o = 0; o < OB; ++o)
 #pragma unroll
-            for (int aa = 0; aa < KH; ++aa)
+                for (int aa = 0; aa < KH; ++aa)
 #pragma unroll
-                for (int b = 0; b < KW; ++b) {
-                    float v = acc[o][aa][b];
-                    for (int off = 1; off < SPw; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                    if ((threadIdx.x & (SPw - 1)) == 0) red[seg * NACC + (o * KH + aa) * KW + b] = v;
-                }
+                    for (int b = 0; b < KW; ++b) acc[o][aa][b] += __shfl_xor_sync(0xffffffffu, acc[o][aa][b], off);
+        }
+        if ((threadIdx.x & (SPw - 1)) == 0) {
+#pragma unroll
+            for (int o = 0; o < OB; ++o)
+#pragma unroll
+                for (int aa = 0; aa < KH; ++aa)
+#pragma unroll
+                    for (int b = 0; b < KW; ++b) red[seg * NACC + (o * KH + aa) * KW + b] = acc[o][aa][b];
+        }
     }
     __syncthreads();
+    if (threadIdx.x == 0) dbg_mark(a.dbg, 3);
 
     // ---- segments -> CTA value per output (fixed order), then CTAs -> dw ----------------------------
     // partial slices are stored in CTA-local order [x][g][z][cl*NACC + idx]: coalesced both ways
@@ -297,17 +309,52 @@ __global__ void __launch_bounds__((max_consumer_warps(OB, KH) + 1) * 32, 1) wgra
         s_last = (ticket == (unsigned)(a.X - 1));
     }
     __syncthreads();
+    if (threadIdx.x == 0) dbg_mark(a.dbg, 4);
     if (!s_last) return;
     __threadfence();
-    // the last CTA of (g, z) sums the X slices per output in fixed order (independent coalesced loads)
-    for (int l = threadIdx.x; l < nloc; l += blockDim.x) {
-        const float* pp = a.partial + slice + l;
-        float v = 0.f;
-#pragma unroll 8
-        for (int xx = 0; xx < a.X; ++xx) v += __ldcg(pp + (long)xx * xstride);
-        finish(l, v);
+    // the last CTA of (g, z) sums the X slices per output.  `parts` threads share one output:
+    // thread (l, q) sums slices q, q+parts, ... (independent coalesced loads, one L2 round trip
+    // for the usual X <= 64), the parts are combined in fixed order through shared memory.
+    {
+        int parts = (int)blockDim.x / nloc;
+        if (parts > 8) parts = 8;
+        if (parts < 1) parts = 1;
+        float* comb = bufs;  // pipeline buffers are free now; needs nloc*parts floats
+        if ((long)nloc * parts > (long)a.S * 2 * half) parts = 1;
+        for (int l0 = 0; l0 < nloc; l0 += (int)blockDim.x / parts) {
+            const int tl = threadIdx.x / parts, q = threadIdx.x - tl * parts;
+            const int l = l0 + tl;
+            float v = 0.f;
+            if (l < nloc && tl < (int)blockDim.x / parts) {
+                const float* pp = a.partial + slice + l;
+                for (int xx0 = q; xx0 < a.X; xx0 += 8 * parts) {  // 8 independent loads in flight
+                    float t8[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int xx = xx0 + u * parts;
+                        t8[u] = xx < a.X ? __ldcg(pp + (long)xx * xstride) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v += t8[u];
+                }
+            }
+            if (parts == 1) {
+                if (l < nloc) finish(l, v);
+            } else {
+                comb[threadIdx.x] = v;
+                __syncthreads();
+                if (q == 0 && l < nloc && tl < (int)blockDim.x / parts) {
+                    float t = 0.f;
+                    for (int qq = 0; qq < parts; ++qq) t += comb[threadIdx.x + qq];
+                    finish(l, t);
+                }
+                __syncthreads();
+            }
+        }
     }
     if (threadIdx.x == 0) a.counters[g * a.Z + zz] = 0u;  // leave the ticket clean
+    __syncthreads();
+    if (threadIdx.x == 0) dbg_mark(a.dbg, 5);
 }
 
 template <int OB, int WT, int KH, int KW>
@@ -366,6 +413,12 @@ bool make_plan(const Shape& s, Plan* p) {
         q.ncombo = s.C * q.nob;
         // CTAs per group first assuming Z = 1
         int xmax = sms / s.G;
+        {
+            const int maxthr0 = max_consumer_warps(ob, s.kH) * 32;
+            const int cpc0 = q.ncombo < maxthr0 ? q.ncombo : maxthr0;  // upper bound of combos per CTA
+            const int xcap0 = 16384 / (cpc0 * ob * s.kH * s.kW);
+            if (xmax > xcap0) xmax = xcap0 < 4 ? 4 : xcap0;
+        }
         if (xmax < 1) xmax = 1;
         int CH = (s.B + xmax - 1) / xmax;  // one chunk per CTA when the batch is small
         const int ch_mem = (int)((budget / 2) / (2 * tile_bytes));  // two tensors, leave half for stages
@@ -398,6 +451,10 @@ bool make_plan(const Shape& s, Plan* p) {
         if ((long)s.G * q.Z * 4 > kCounterBytes) continue;
         q.nchunks = (s.B + CH - 1) / CH;
         int x = sms / (s.G * q.Z);
+        // the last CTA of a (g,z) slice sums X partial vectors of cpc*NACC floats: keep that tail
+        // to ~one batch of loads per thread
+        const int xcap = 16384 / (q.cpc * ob * s.kH * s.kW);
+        if (x > xcap) x = xcap < 4 ? 4 : xcap;
         if (x < 1) x = 1;
         q.X = x < q.nchunks ? x : q.nchunks;
         const int cpcta = (q.nchunks + q.X - 1) / q.X;
@@ -440,7 +497,7 @@ int launch_wgrad_fast(const float* dz, const float* x, float* dw, float* workspa
     if (!make_plan(s, &p)) return 0;
     if (ws_floats < kCounterBytes / 4 + partial_floats(s, p)) return FINC_E_WORKSPACE;
     WgArgs a{};
-    a.dz = dz; a.x = x; a.dw = dw; a.s = s; a.flags = flags;
+    a.dz = dz; a.x = x; a.dw = dw; a.s = s; a.flags = flags; a.dbg = debug_ts_buffer();
     a.counters = reinterpret_cast<unsigned*>(workspace);
     a.partial = workspace + kCounterBytes / 4;
     a.CH = p.CH; a.S = p.S; a.nob = p.nob; a.nstrip = p.nstrip; a.RR = p.RR; a.rpr = p.rpr;

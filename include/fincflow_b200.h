@@ -131,6 +131,10 @@ int finc_logdet_f32(const float* w, float* logdet, int B, int G, int C, int H, i
 int finc_gaussian_logp_f32(const float* z, const float* logdet, float* logp, float* dz, float dz_scale,
                            int B, long D, void* stream);
 
+/* Debug aid, inactive unless the environment has FINC_DEBUG_TS=1: the tiled kernels then record
+ * per-CTA %globaltimer marks (8 slots per CTA); this call synchronises the device and copies them. */
+int finc_debug_timestamps(unsigned long long* host_out, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,16 +65,19 @@ int launch_inverse_wave(const float* z, const float* w, float* x, const Shape& s
     if (items_per_cta > nwarps && (size_t)nwarps * 2 * (stage_bytes + 8) <= avail) a.S = 2;
     const size_t smem = wk_bytes + (size_t)nwarps * a.S * (stage_bytes + 8) + 16;
     dim3 grid((unsigned)ctas, a.gsplit ? s.G : 1, 1);
-    *handled = true;
+    int rc;
     switch (C) {
-        case 1: return wave::dispatch_c<1>(s.kH, P, a, grid, nwarps * 32, smem, st);
-        case 2: return wave::dispatch_c<2>(s.kH, P, a, grid, nwarps * 32, smem, st);
-        case 3: return wave::dispatch_c<3>(s.kH, P, a, grid, nwarps * 32, smem, st);
-        case 4: return wave::dispatch_c<4>(s.kH, P, a, grid, nwarps * 32, smem, st);
-        case 6: return wave::dispatch_c<6>(s.kH, P, a, grid, nwarps * 32, smem, st);
-        case 12: return wave::dispatch_c<12>(s.kH, P, a, grid, nwarps * 32, smem, st);
-        default: return wave::dispatch_c<24>(s.kH, P, a, grid, nwarps * 32, smem, st);
+        case 1: rc = wave::dispatch_c<1>(s.kH, P, a, grid, nwarps * 32, smem, st); break;
+        case 2: rc = wave::dispatch_c<2>(s.kH, P, a, grid, nwarps * 32, smem, st); break;
+        case 3: rc = wave::dispatch_c<3>(s.kH, P, a, grid, nwarps * 32, smem, st); break;
+        case 4: rc = wave::dispatch_c<4>(s.kH, P, a, grid, nwarps * 32, smem, st); break;
+        case 6: rc = wave::dispatch_c<6>(s.kH, P, a, grid, nwarps * 32, smem, st); break;
+        case 12: rc = wave::dispatch_c<12>(s.kH, P, a, grid, nwarps * 32, smem, st); break;
+        default: rc = wave::dispatch_c<24>(s.kH, P, a, grid, nwarps * 32, smem, st); break;
     }
+    if (rc == FINC_E_UNSUPPORTED) return 0;  // combination not instantiated: generic tiled kernel
+    *handled = true;
+    return rc;
 }
 
 }  // namespace finc

@@ -366,14 +366,20 @@ int launch_inst(const WaveArgs& a, dim3 grid, int threads, size_t smem, cudaStre
     return (int)cudaGetLastError();
 }
 
+// parts-per-pixel variants instantiated per channel count: wide tiles (small P) only occur
+// with few channels, so the heavily unrolled (large C, small P) combinations are left to the
+// generic tiled kernel
 template <int C, int KH, int KW>
 int dispatch_p(int P, const WaveArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-    switch (P) {
-        case 1: return launch_inst<C, KH, KW, 1>(a, grid, threads, smem, st);
-        case 2: return launch_inst<C, KH, KW, 2>(a, grid, threads, smem, st);
-        case 4: return launch_inst<C, KH, KW, 4>(a, grid, threads, smem, st);
-        default: return launch_inst<C, KH, KW, 8>(a, grid, threads, smem, st);
+    if constexpr (C <= 6) {
+        if (P == 1) return launch_inst<C, KH, KW, 1>(a, grid, threads, smem, st);
     }
+    if constexpr (C <= 12) {
+        if (P == 2) return launch_inst<C, KH, KW, 2>(a, grid, threads, smem, st);
+    }
+    if (P == 4) return launch_inst<C, KH, KW, 4>(a, grid, threads, smem, st);
+    if (P == 8) return launch_inst<C, KH, KW, 8>(a, grid, threads, smem, st);
+    return FINC_E_UNSUPPORTED;
 }
 
 // per-channel-count dispatch; explicitly instantiated in finc_inverse_wave_c<N>.cu so the

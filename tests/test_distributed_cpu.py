@@ -1,0 +1,93 @@
+"""CPU tests (gloo, world_size 2) of the data-parallel host logic: batch sharding and the
+flat-bucket all-reduce reproduce the global-batch gradient of the reference's CPU path."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import rel_err
+
+
+def test_shard_range_partitions():
+    from fincflow_b200.distributed import shard_range
+
+    for n in (0, 1, 7, 256, 257):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from fincflow_b200 import distributed as fd
+    from fincflow_b200.stack import LevelSpec
+    from oracle.reference_path import ReferenceCpuStack
+
+    torch.set_num_threads(1)
+    pg = fd.init_process_group("gloo")
+    assert fd.dp_env() == (rank, world, rank)
+    lv = [LevelSpec(12, 6, 6, 2, (3, 3))]
+    B = 6
+    full = ReferenceCpuStack(lv, B, seed=3, lr=0.0, threads=1)       # identical on every rank
+    lo, hi = fd.shard_range(B, rank, world)
+    # local loss = -sum(logp_local) * loss_scale  ->  SUM over ranks == global mean loss gradient
+    flat = []
+    for u, w in enumerate(full.weights[0]):
+        w.grad = None
+    h = full.x[0][lo:hi]
+    from oracle.reference_path import unit_forward
+    import math
+
+    for w in full.weights[0]:
+        h = unit_forward(h, w)
+    logp = -0.5 * h.flatten(1).pow(2).sum(1) - 0.5 * lv[0].dim * math.log(2 * math.pi)
+    (-(logp.sum()) * fd.loss_scale(hi - lo, world) * ((hi - lo) * world / B)).backward()
+    bucket = torch.cat([(w.grad * full.masks[0]).flatten() for w in full.weights[0]])
+    fd.allreduce_sum_(bucket, pg)
+    if rank == 0:
+        out.put(bucket.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_allreduce_equals_global_gradient():
+    from fincflow_b200.stack import LevelSpec
+    from oracle.reference_path import ReferenceCpuStack, unit_forward
+    import math
+
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = out.get()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    lv = [LevelSpec(12, 6, 6, 2, (3, 3))]
+    B = 6
+    full = ReferenceCpuStack(lv, B, seed=3, lr=0.0, threads=1)
+    h = full.x[0]
+    for w in full.weights[0]:
+        h = unit_forward(h, w)
+    logp = -0.5 * h.flatten(1).pow(2).sum(1) - 0.5 * lv[0].dim * math.log(2 * math.pi)
+    (-logp.sum() / B).backward()
+    want = torch.cat([(w.grad * full.masks[0]).flatten() for w in full.weights[0]]).numpy()
+    assert rel_err(got, want) <= 1e-5
+
+
+def test_compat_shims_have_the_pybind_signature():
+    import inspect
+
+    from fincflow_b200 import compat
+
+    for obj in (compat.cinc_cuda_level1, compat.cinc_cuda_level2):
+        assert list(inspect.signature(obj.inverse).parameters) == ["input", "kernel", "output"]

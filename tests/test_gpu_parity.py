@@ -273,3 +273,36 @@ def test_layers_autograd_and_reference_conventions(nat):
         assert zero == 0 and (y - xc.detach()).abs().max().item() <= RT_TOL
         wn = conv.conv.weight.detach().cpu().numpy()
         assert rel_err(zc.detach().cpu().numpy(), fo.forward(xc.detach().cpu().numpy(), wn, (order,))) <= REL_TOL
+
+
+def test_reference_pybind_call_site_runs_on_the_shim(nat):
+    """FastFlowUnit.reverse_level2 of the reference (fastflow/fastflow.py:78-100), restated
+    line by line, calling the drop-in for its pybind `cinc_cuda_level2.inverse`."""
+    from fincflow_b200 import compat
+    from fincflow_b200.fastflow import FastFlowUnit
+
+    torch.manual_seed(7)
+    unit = FastFlowUnit(24, 24, (3, 3)).cuda()
+    x = torch.randn(5, 24, 8, 8, device="cuda")
+    z, _ = unit(x)
+    w = [unit.conv_tl.conv.weight, unit.conv_tr.conv.weight, unit.conv_bl.conv.weight, unit.conv_br.conv.weight]
+    k_tl, k_tr = w[0].data, torch.flip(w[1].data, [3])
+    k_bl, k_br = torch.flip(w[2].data, [2]), torch.flip(w[3].data, [2, 3])
+    kernel = torch.cat([k_tl, k_tr, k_bl, k_br], dim=0).contiguous()
+    o_tl, o_tr, o_bl, o_br = torch.chunk(z.detach(), 4, dim=1)
+    xin = torch.cat([o_tl, torch.flip(o_tr, [3]), torch.flip(o_bl, [2]), torch.flip(o_br, [2, 3])], dim=1).contiguous()
+    y = torch.zeros_like(xin)
+    y = compat.cinc_cuda_level2.inverse(xin, kernel, y)[0]
+    o_tl, o_tr, o_bl, o_br = torch.chunk(y, 4, dim=1)
+    y = torch.cat([o_tl, torch.flip(o_tr, [3]), torch.flip(o_bl, [2]), torch.flip(o_br, [2, 3])], dim=1)
+    assert (y - x).abs().max().item() <= RT_TOL
+    assert rel_err(y.cpu().numpy(), unit.reverse(z.detach()).cpu().numpy()) <= REL_TOL
+    # level-1 shim: one TL-form convolution over all channels (layers/conv.py:191-218)
+    from fincflow_b200.layers.conv import PaddedConv2d
+
+    conv = PaddedConv2d(4, 4, (3, 3), order="BR").cuda()
+    xc = torch.randn(3, 4, 14, 14, device="cuda")
+    zc, _ = conv(xc)
+    kern = torch.flip(conv.conv.weight.data, [2, 3]).contiguous()
+    yc = compat.cinc_cuda_level1.inverse(torch.flip(zc.detach(), [2, 3]).contiguous(), kern, torch.zeros_like(xc))[0]
+    assert (torch.flip(yc, [2, 3]) - xc).abs().max().item() <= RT_TOL

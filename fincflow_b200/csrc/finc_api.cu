@@ -22,6 +22,15 @@ unsigned long long* debug_ts_buffer() {
     return static_cast<unsigned long long*>(p);
 }
 
+int pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FINC_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
+}
+
 static int g_sm_count[64];
 static size_t g_smem_optin[64];
 

@@ -139,6 +139,32 @@ __device__ __forceinline__ void dbg_mark(unsigned long long* buf, int slot) {
 }
 unsigned long long* debug_ts_buffer();  // device pointer, or nullptr when disabled
 
+// Programmatic dependent launch (PDL): a kernel launched with the attribute may start while
+// its stream predecessor is still draining.  pdl_wait() blocks until the predecessor has
+// completed and its memory is visible -- it must precede the first global access; everything
+// before it (barrier init, index math) overlaps the predecessor's tail.  pdl_trigger() lets the
+// successor start launching.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+int pdl_enabled();  // FINC_PDL=0 disables (default on)
+
+// kernel launch with the PDL attribute (plain launch when disabled)
+template <typename Kern, typename Args>
+inline int launch_kernel(Kern kern, dim3 grid, int threads, size_t smem, cudaStream_t st, const Args& a) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3((unsigned)threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return (int)cudaLaunchKernelEx(&cfg, kern, a);
+}
+
 __device__ __forceinline__ bool is_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---------------------------------------------------------------------------------------

@@ -243,6 +243,10 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kern
             mbar_init(&empty[st], nthreads_c >> 5);
         }
         fence_mbar_init();
+    }
+    pdl_wait();     // predecessor (producer of x / last writer of y) has completed
+    pdl_trigger();  // successor may start its own prologue
+    if (a.bulk && is_producer && lane == 0) {
         for (int st = 0; st < a.S; ++st) {
             const long chunk = blockIdx.x + (long)st * gridDim.x;
             if (chunk < a.n_chunks) issue_load(chunk, st);
@@ -356,8 +360,7 @@ int launch_inst(const ConvArgs& a, dim3 grid, int threads, size_t smem, cudaStre
     auto kern = conv_cta_kernel<CT, OB, WT, KH, KW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    kern<<<grid, threads, smem, st>>>(a);
-    return (int)cudaGetLastError();
+    return launch_kernel(kern, grid, threads, smem, st, a);
 }
 
 template <int CT, int OB, int WT>

@@ -95,6 +95,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
     if (a.bulk && lane == 0) {
         for (int st = 0; st < a.S; ++st) mbar_init(&bars[st], 1);
         fence_mbar_init();
+    }
+    pdl_wait();
+    pdl_trigger();
+    if (a.bulk && lane == 0) {
         for (int st = 0; st < n_pre; ++st) {
             const long item = gw + st * gstride;
             if (item < a.n_items) issue_load(item, st);
@@ -362,8 +366,7 @@ int launch_inst(const WaveArgs& a, dim3 grid, int threads, size_t smem, cudaStre
     auto kern = inverse_wave_kernel<C, KH, KW, P>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    kern<<<grid, threads, smem, st>>>(a);
-    return (int)cudaGetLastError();
+    return launch_kernel(kern, grid, threads, smem, st, a);
 }
 
 // parts-per-pixel variants instantiated per channel count: wide tiles (small P) only occur

@@ -172,6 +172,10 @@ __global__ void __launch_bounds__((max_consumer_warps(OB, KH) + 1) * 32, 1) wgra
             mbar_init(&empty[st], nthreads_c >> 5);
         }
         fence_mbar_init();
+    }
+    pdl_wait();
+    pdl_trigger();
+    if (a.bulk && is_producer && lane == 0) {
         for (int st = 0; st < a.S; ++st) {
             const int chunk = blockIdx.x + st * a.X;
             if (chunk < a.nchunks) issue(chunk, st);
@@ -362,8 +366,7 @@ int launch_inst(const WgArgs& a, dim3 grid, int threads, size_t smem, cudaStream
     auto kern = wgrad_kernel<OB, WT, KH, KW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    kern<<<grid, threads, smem, st>>>(a);
-    return (int)cudaGetLastError();
+    return launch_kernel(kern, grid, threads, smem, st, a);
 }
 
 template <int OB, int WT>

@@ -146,7 +146,8 @@ class HotPathRunner:
     kernel) -> optimizer step; sampling is model.sample (train/experiment.py:327-337).
     """
 
-    PHASES = ("forward_logdet", "backward_input", "backward_weight", "optimizer", "inverse")
+    PHASES = ("forward_logdet", "backward", "optimizer", "inverse")
+    N_SIDE = 4  # side streams for the mutually independent weight-gradient launches
 
     def __init__(self, stack: FincStack, batch: int, device, slots=1, lr=1e-3, host_io=False,
                  process_group=None, use_graphs=True):
@@ -161,7 +162,10 @@ class HotPathRunner:
         for lv in stack.levels:
             ws = max(ws, _native.backward_weight_workspace_bytes(batch, 4, lv.cq, lv.height, lv.width,
                                                                  *lv.kernel_size))
-        self.workspace = _native.new_workspace(ws, self.device)
+        # the dW launches of different units are independent: fan them out over side streams
+        # (one reduction workspace per stream: calls sharing a workspace must be stream-ordered)
+        self.side = [torch.cuda.Stream(self.device) for _ in range(self.N_SIDE)]
+        self.workspaces = [_native.new_workspace(ws, self.device) for _ in range(self.N_SIDE)]
         self.slots = [_Slot(stack, batch, self.device, host_io) for _ in range(slots)]
         self.graphs = [None] * slots
         self.launches_per_step = None
@@ -170,6 +174,13 @@ class HotPathRunner:
     # ---- the four phases as plain launch sequences on the current stream ----------------------
     def _forward(self, s):
         st = self.stack
+        main = torch.cuda.current_stream(self.device)
+        if self.host_io:
+            # latents for the sampling pass travel while the train step computes
+            self.copy_stream.wait_stream(main)
+            with torch.cuda.stream(self.copy_stream):
+                for li in range(len(st.levels)):
+                    s.zin[li].copy_(s.z_host[li], non_blocking=True)
         for li, lv in enumerate(st.levels):
             if self.host_io:
                 s.acts[li][0].copy_(s.x_host[li], non_blocking=True)
@@ -182,21 +193,33 @@ class HotPathRunner:
                                   logp_out=s.logp[li], dz_out=s.dzs[li][lv.n_units])
             if self.host_io:
                 s.logp_host[li].copy_(s.logp[li], non_blocking=True)
+        if self.host_io:
+            main.wait_stream(self.copy_stream)
 
-    def _backward_input(self, s):
-        """dzs[u] = dL/d acts[u] for u = n-1 .. 1 (the data gradient of unit 0 is never needed)"""
+    def _backward(self, s):
+        """dX chain on the current stream; the masked dW of every unit -- written straight into
+        the flat gradient bucket -- on side streams as soon as its dz exists.
+        dzs[u] = dL/d acts[u]; the data gradient of unit 0 is never needed."""
         st = self.stack
+        main = torch.cuda.current_stream(self.device)
+        k = 0
         for li, lv in enumerate(st.levels):
-            for u in reversed(range(1, lv.n_units)):
-                _native.backward_input(s.dzs[li][u + 1], st.unit_weight(li, u).detach(), out=s.dzs[li][u])
-
-    def _backward_weight(self, s):
-        """masked dW of every unit, written straight into the flat gradient bucket"""
-        st = self.stack
-        for li, lv in enumerate(st.levels):
-            for u in range(lv.n_units):
-                _native.backward_weight(s.dzs[li][u + 1], s.acts[li][u], lv.kernel_size,
-                                        out=st.unit_weight(li, u, self.grad), workspace=self.workspace)
+            ready = torch.cuda.Event()
+            ready.record(main)                      # dzs[n] comes from the forward phase
+            for u in reversed(range(lv.n_units)):
+                side = self.side[k % self.N_SIDE]
+                side.wait_event(ready)
+                with torch.cuda.stream(side):
+                    _native.backward_weight(s.dzs[li][u + 1], s.acts[li][u], lv.kernel_size,
+                                            out=st.unit_weight(li, u, self.grad),
+                                            workspace=self.workspaces[k % self.N_SIDE])
+                k += 1
+                if u > 0:
+                    _native.backward_input(s.dzs[li][u + 1], st.unit_weight(li, u).detach(), out=s.dzs[li][u])
+                    ready = torch.cuda.Event()
+                    ready.record(main)
+        for side in self.side:
+            main.wait_stream(side)
 
     def _optimizer(self, s):
         if self.world > 1:
@@ -206,8 +229,6 @@ class HotPathRunner:
     def _inverse(self, s):
         st = self.stack
         for li, lv in enumerate(st.levels):
-            if self.host_io:
-                s.zin[li].copy_(s.z_host[li], non_blocking=True)
             src, cur = s.zin[li], 0
             for u in reversed(range(lv.n_units)):
                 _native.inverse(src, st.unit_weight(li, u).detach(), out=s.samp[li][cur])
@@ -218,7 +239,7 @@ class HotPathRunner:
             s.sample_out[li] = src
 
     def _phase_fns(self):
-        return (self._forward, self._backward_input, self._backward_weight, self._optimizer, self._inverse)
+        return (self._forward, self._backward, self._optimizer, self._inverse)
 
     # ---- graphs -------------------------------------------------------------------------------
     def prepare(self):

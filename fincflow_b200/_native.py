@@ -24,13 +24,15 @@ FLAG_ACCUMULATE = 4
 FLAG_LOGDET_ACCUMULATE = 8
 FLAG_GENERIC_TILED = 16
 FLAG_WORKSPACE_CLEAN = 32
+FLAG_PREPARED = 64
+PREP_FORWARD, PREP_BACKWARD_INPUT, PREP_INVERSE = 0, 1, 2
 
 # every symbol declared in include/fincflow_b200.h
 SYMBOLS = (
     "finc_abi_version", "finc_error_string", "finc_set_device", "finc_sm_count",
     "finc_forward_f32", "finc_backward_input_f32", "finc_backward_weight_workspace_bytes",
     "finc_backward_weight_f32", "finc_inverse_f32", "finc_apply_grad_mask_f32", "finc_logdet_f32",
-    "finc_gaussian_logp_f32", "finc_debug_timestamps",
+    "finc_gaussian_logp_f32", "finc_debug_timestamps", "finc_prepared_weights_bytes", "finc_prepare_weights_f32",
 )
 
 _lib = None
@@ -68,6 +70,10 @@ def load():
     lib.finc_apply_grad_mask_f32.argtypes = [p, i, i, i, i, u, p]
     lib.finc_logdet_f32.argtypes = [p, p, *dims, u, p]
     lib.finc_gaussian_logp_f32.argtypes = [p, p, p, p, ctypes.c_float, i, ctypes.c_long, p]
+    lib.finc_prepared_weights_bytes.restype = sz
+    lib.finc_prepared_weights_bytes.argtypes = [i] + dims
+    lib.finc_prepare_weights_f32.restype = i
+    lib.finc_prepare_weights_f32.argtypes = [p, p, i, i, sz, sz, *dims, u, p]
     for f in ("finc_set_device", "finc_forward_f32", "finc_backward_input_f32", "finc_backward_weight_f32",
               "finc_inverse_f32", "finc_apply_grad_mask_f32", "finc_logdet_f32", "finc_gaussian_logp_f32"):
         getattr(lib, f).restype = i
@@ -121,11 +127,22 @@ def _dims(x: torch.Tensor, w: torch.Tensor, G: int):
     return B, G, C, H, W, int(w.shape[2]), int(w.shape[3])
 
 
-def forward(x, w, G=4, orders=ORDERS_UNIT, want_logdet=True, flags=0, out=None, logdet_out=None):
+def _dims_prepared(x, G, ksize):
+    B, CT, H, W = x.shape
+    return B, G, CT // G, H, W, int(ksize[0]), int(ksize[1])
+
+
+def forward(x, w, G=4, orders=ORDERS_UNIT, want_logdet=True, flags=0, out=None, logdet_out=None, prepared=None,
+            ksize=None):
     """z, logdet[B] (or None).  C ABI: finc_forward_f32.  With `logdet_out` and
-    FLAG_LOGDET_ACCUMULATE the layer's logdet is added into a running [B] accumulator."""
-    x, w = _prep(x, "x"), _prep(w, "weight")
-    d = _dims(x, w, G)
+    FLAG_LOGDET_ACCUMULATE the layer's logdet is added into a running [B] accumulator.
+    `prepared` (a table from prepare_weights, with `ksize`) replaces `w`; no logdet then."""
+    x = _prep(x, "x")
+    if prepared is not None:
+        d, w, flags = _dims_prepared(x, G, ksize), prepared, flags | FLAG_PREPARED
+    else:
+        w = _prep(w, "weight")
+        d = _dims(x, w, G)
     _bind_device(x)
     z = torch.empty_like(x) if out is None else out
     if logdet_out is not None:
@@ -138,9 +155,13 @@ def forward(x, w, G=4, orders=ORDERS_UNIT, want_logdet=True, flags=0, out=None, 
     return z, logdet
 
 
-def backward_input(dz, w, G=4, orders=ORDERS_UNIT, flags=0, out=None):
-    dz, w = _prep(dz, "dz"), _prep(w, "weight")
-    d = _dims(dz, w, G)
+def backward_input(dz, w, G=4, orders=ORDERS_UNIT, flags=0, out=None, prepared=None, ksize=None):
+    dz = _prep(dz, "dz")
+    if prepared is not None:
+        d, w, flags = _dims_prepared(dz, G, ksize), prepared, flags | FLAG_PREPARED
+    else:
+        w = _prep(w, "weight")
+        d = _dims(dz, w, G)
     _bind_device(dz)
     dx = torch.empty_like(dz) if out is None else out
     _check(load().finc_backward_input_f32(dz.data_ptr(), w.data_ptr(), dx.data_ptr(), *d, orders, flags,
@@ -183,9 +204,13 @@ def backward_weight(dz, x, ksize, G=4, orders=ORDERS_UNIT, flags=0, out=None, wo
     return out
 
 
-def inverse(z, w, G=4, orders=ORDERS_UNIT, flags=0, out=None):
-    z, w = _prep(z, "z"), _prep(w, "weight")
-    d = _dims(z, w, G)
+def inverse(z, w, G=4, orders=ORDERS_UNIT, flags=0, out=None, prepared=None, ksize=None):
+    z = _prep(z, "z")
+    if prepared is not None:
+        d, w, flags = _dims_prepared(z, G, ksize), prepared, flags | FLAG_PREPARED
+    else:
+        w = _prep(w, "weight")
+        d = _dims(z, w, G)
     _bind_device(z)
     x = torch.empty_like(z) if out is None else out
     _check(load().finc_inverse_f32(z.data_ptr(), w.data_ptr(), x.data_ptr(), *d, orders, flags, _stream(z)),
@@ -228,6 +253,22 @@ def gaussian_logp(z, logdet=None, dz_scale=None, logp_out=None, dz_out=None):
                                          None if dz is None else dz.data_ptr(), float(dz_scale or 0.0), B, D,
                                          _stream(z)), "finc_gaussian_logp_f32")
     return logp, dz
+
+
+def prepared_weights_bytes(kind, B, G, C, H, W, kH, kW) -> int:
+    """bytes of one unit's prepared table; 0 = shape not covered (do not use FLAG_PREPARED)"""
+    return int(load().finc_prepared_weights_bytes(kind, B, G, C, H, W, kH, kW))
+
+
+def prepare_weights(w_units, tables, kind, B, H, W, G=4, orders=ORDERS_UNIT):
+    """w_units: [n_units, G*C, C, kH, kW] contiguous; tables: [n_units, bytes] uint8 -> filled in ONE launch"""
+    w_units = _prep(w_units, "weights")
+    _bind_device(w_units)
+    n = int(w_units.shape[0])
+    C, kH, kW = int(w_units.shape[2]), int(w_units.shape[3]), int(w_units.shape[4])
+    _check(load().finc_prepare_weights_f32(w_units.data_ptr(), tables.data_ptr(), kind, n, w_units.stride(0), tables.stride(0),
+                                           B, G, C, H, W, kH, kW, orders, _stream(w_units)), "finc_prepare_weights_f32")
+    return tables
 
 
 def sm_count() -> int:

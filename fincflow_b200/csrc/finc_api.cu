@@ -108,9 +108,12 @@ int finc_forward_f32(const float* x, const float* w, float* z, float* logdet, in
     cudaStream_t st = (cudaStream_t)stream;
     int rc = 0;
     bool handled = false;
-    if (!(flags & FINC_FLAG_NAIVE)) rc = launch_conv_fast(x, w, z, logdet, (flags & FINC_FLAG_LOGDET_ACCUMULATE) != 0, s, false, st, &handled);
+    const bool prep = (flags & FINC_FLAG_PREPARED) != 0;
+    if (prep && (flags & FINC_FLAG_NAIVE)) return FINC_E_BADARG;
+    if (!(flags & FINC_FLAG_NAIVE)) rc = launch_conv_fast(x, w, z, logdet, (flags & FINC_FLAG_LOGDET_ACCUMULATE) != 0, s, false, prep, st, &handled);
     if (rc) return rc;
     if (handled) return FINC_OK;  // logdet was written by the fused epilogue
+    if (prep) return FINC_E_UNSUPPORTED;  // the generic kernels need the raw weights
     rc = launch_conv_naive(x, w, z, s, false, st);
     if (rc) return rc;
     if (logdet) rc = launch_logdet(w, logdet, (flags & FINC_FLAG_LOGDET_ACCUMULATE) != 0, s, st);
@@ -126,8 +129,11 @@ int finc_backward_input_f32(const float* dz, const float* w, float* dx, int B, i
     cudaStream_t st = (cudaStream_t)stream;
     int rc = 0;
     bool handled = false;
-    if (!(flags & FINC_FLAG_NAIVE)) rc = launch_conv_fast(dz, w, dx, nullptr, false, s, true, st, &handled);
+    const bool prep = (flags & FINC_FLAG_PREPARED) != 0;
+    if (prep && (flags & FINC_FLAG_NAIVE)) return FINC_E_BADARG;
+    if (!(flags & FINC_FLAG_NAIVE)) rc = launch_conv_fast(dz, w, dx, nullptr, false, s, true, prep, st, &handled);
     if (rc) return rc;
+    if (prep && !handled) return FINC_E_UNSUPPORTED;
     if (!handled) rc = launch_conv_naive(dz, w, dx, s, true, st);
     return rc;
 }
@@ -165,8 +171,10 @@ int finc_inverse_f32(const float* z, const float* w, float* x, int B, int G, int
     int rc = 0;
     bool handled = false;
     if (!(flags & FINC_FLAG_NAIVE)) {
-        if (!(flags & FINC_FLAG_GENERIC_TILED)) rc = launch_inverse_wave(z, w, x, s, st, &handled);
+        const bool prep = (flags & FINC_FLAG_PREPARED) != 0;
+        if (!(flags & FINC_FLAG_GENERIC_TILED)) rc = launch_inverse_wave(z, w, x, s, prep, st, &handled);
         if (rc) return rc;
+        if (prep && !handled) return FINC_E_UNSUPPORTED;
         if (!handled) rc = launch_inverse_fast(z, w, x, s, st, &handled);
     }
     if (rc) return rc;
@@ -195,13 +203,41 @@ int finc_gaussian_logp_f32(const float* z, const float* logdet, float* logp, flo
     return launch_gaussian_logp(z, logdet, logp, dz, dz_scale, B, D, (cudaStream_t)stream);
 }
 
+size_t finc_prepared_weights_bytes(int kind, int B, int G, int C, int H, int W, int kH, int kW) {
+    if (!shape_ok(B, G, C, H, W, kH, kW) || B < 1) return 0;
+    const Shape s = mk(B, G, C, H, W, kH, kW, 0);
+    size_t f = 0;
+    if (kind == FINC_PREP_FORWARD || kind == FINC_PREP_BACKWARD_INPUT) f = conv_prepared_floats(s);
+    else if (kind == FINC_PREP_INVERSE) f = wave_prepared_floats(s);
+    return ((f * sizeof(float) + 127) / 128) * 128;
+}
+
+int finc_prepare_weights_f32(const float* w, void* prepared, int kind, int n_units, size_t w_stride_floats,
+                             size_t prepared_stride_bytes, int B, int G, int C, int H, int W, int kH, int kW,
+                             unsigned orders, void* stream) {
+    if (!shape_ok(B, G, C, H, W, kH, kW) || !w || !prepared || n_units < 1 || prepared_stride_bytes % 16 != 0 ||
+        (reinterpret_cast<uintptr_t>(prepared) & 15) != 0)
+        return FINC_E_BADARG;
+    const Shape s = mk(B, G, C, H, W, kH, kW, orders);
+    float* out = static_cast<float*>(prepared);
+    const size_t ostride = prepared_stride_bytes / sizeof(float);
+    if (kind == FINC_PREP_FORWARD) return launch_conv_prepare(w, out, n_units, w_stride_floats, ostride, s, false, (cudaStream_t)stream);
+    if (kind == FINC_PREP_BACKWARD_INPUT) return launch_conv_prepare(w, out, n_units, w_stride_floats, ostride, s, true, (cudaStream_t)stream);
+    if (kind == FINC_PREP_INVERSE) return launch_wave_prepare(w, out, n_units, w_stride_floats, ostride, s, (cudaStream_t)stream);
+    return FINC_E_BADARG;
+}
+
 /* debug only (FINC_DEBUG_TS=1): copy the per-CTA timestamp marks of the last launch (synchronises) */
 int finc_debug_timestamps(unsigned long long* host_out, int n) {
     if (!host_out || n <= 0) return FINC_E_BADARG;
     if (n > kDbgCtas * kDbgSlots) n = kDbgCtas * kDbgSlots;
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return (int)e;
-    return (int)cudaMemcpyFromSymbol(host_out, g_finc_dbg, sizeof(unsigned long long) * n);
+    e = cudaMemcpyFromSymbol(host_out, g_finc_dbg, sizeof(unsigned long long) * n);
+    if (e != cudaSuccess) return (int)e;
+    void* p = nullptr;
+    if (cudaGetSymbolAddress(&p, g_finc_dbg) == cudaSuccess) cudaMemset(p, 0, sizeof(g_finc_dbg));  // fresh marks next time
+    return 0;
 }
 
 }  // extern "C"

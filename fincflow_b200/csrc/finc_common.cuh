@@ -175,9 +175,17 @@ size_t max_optin_smem_cached();
 
 // launchers implemented by the per-kernel translation units; all return cudaError_t as int
 int launch_conv_fast(const float* x, const float* w, float* y, float* logdet, bool logdet_acc, const Shape& s,
-                     bool transpose, cudaStream_t st, bool* handled);
+                     bool transpose, bool prepared, cudaStream_t st, bool* handled);
+size_t conv_prepared_floats(const Shape& s);
+int launch_conv_prepare(const float* w, float* out, int n_units, size_t w_stride, size_t out_stride, const Shape& s,
+                        bool transpose, cudaStream_t st);
 int launch_inverse_fast(const float* z, const float* w, float* x, const Shape& s, cudaStream_t st, bool* handled);
-int launch_inverse_wave(const float* z, const float* w, float* x, const Shape& s, cudaStream_t st, bool* handled);
+int launch_inverse_wave(const float* z, const float* w, float* x, const Shape& s, bool prepared, cudaStream_t st,
+                        bool* handled);
+size_t wave_prepared_floats(const Shape& s);
+int launch_wave_prepare(const float* w, float* out, int n_units, size_t w_stride, size_t out_stride, const Shape& s,
+                        cudaStream_t st);
+constexpr int kPrepHeaderFloats = 32;  // 128-byte header in front of a prepared table
 int launch_wgrad_fast(const float* dz, const float* x, float* dw, float* workspace, size_t ws_floats, const Shape& s,
                       unsigned flags, cudaStream_t st, bool* handled);
 size_t wgrad_workspace_floats(const Shape& s);

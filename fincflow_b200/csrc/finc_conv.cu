@@ -23,7 +23,7 @@ int pick_ob(int ct, int C, long rows_strips_per_tile, long tiles_per_cta) {
         case 3: cands[n++] = 3; cands[n++] = 1; break;
         case 4: cands[n++] = 4; cands[n++] = 2; break;
         case 6: cands[n++] = 6; cands[n++] = 3; cands[n++] = 2; break;
-        case 12: case 24: cands[n++] = 4; cands[n++] = 2; break;
+        case 12: case 24: cands[n++] = 4; cands[n++] = 2; cands[n++] = 1; break;
         default:  // generic: any divisor among {6,4,3,2,1}; 4 with a padded last block for C > 6
             for (int ob : {6, 4, 3, 2, 1}) {
                 if (ob > C) continue;
@@ -44,42 +44,124 @@ unsigned magic(unsigned d) { return d <= 1 ? 0u : (unsigned)(((1ull << 32) + d -
 
 }  // namespace
 
+// everything about the weight table that does not depend on pointers or the batch split
+struct WeightPlan {
+    int ct, OB, OBP, nob, gsplit, WTn;
+    size_t wk_per_g;
+};
+
+static bool plan_weights(const Shape& s, WeightPlan* p) {
+    if (!(s.kH == s.kW && (s.kH == 3 || s.kH == 5 || s.kH == 2))) return false;
+    if ((long)s.C * s.H * s.W * 4 > 48 * 1024) return false;
+    p->WTn = s.W % 4 == 0 ? 4 : (s.W % 2 == 0 ? 2 : 1);  // nominal strip width (aligned tensors)
+    p->ct = 0;
+    if ((s.kH == 3 || s.kH == 5) && p->WTn >= 2)
+        for (int c : {1, 2, 3, 4, 6, 12, 24})
+            if (s.C == c) p->ct = c;
+    const int sms = sm_count_cached();
+    const size_t smem_max = max_optin_smem_cached();
+    const size_t budget = smem_max > 8192 ? smem_max - 4096 : 0;
+    p->gsplit = ((size_t)s.G * s.C * s.C * s.kH * s.kW * 4 * 4 / 3 > budget / 2) ? 1 : 0;
+    const long n_tiles = p->gsplit ? s.B : (long)s.B * s.G;
+    long ctas_max = p->gsplit ? sms / s.G : sms;
+    if (ctas_max < 1) ctas_max = 1;
+    const long spread = (n_tiles + ctas_max - 1) / ctas_max;
+    p->OB = pick_ob(p->ct, s.C, (long)s.H * (s.W / p->WTn), spread);
+    p->OBP = p->OB <= 2 ? p->OB : ((p->OB + 3) / 4) * 4;
+    p->nob = (s.C + p->OB - 1) / p->OB;
+    p->wk_per_g = (size_t)s.C * s.kH * s.kW * p->nob * p->OBP;
+    if ((p->gsplit ? p->wk_per_g : p->wk_per_g * s.G) * 4 > budget / 2) return false;
+    return true;
+}
+
+size_t conv_prepared_floats(const Shape& s) {
+    WeightPlan p;
+    if (!plan_weights(s, &p)) return 0;
+    if ((p.gsplit ? p.wk_per_g : p.wk_per_g * s.G) % 4 != 0) return 0;  // bulk copies move 16-byte multiples
+    if (((long)s.C * s.H * s.W) % 4 != 0) return 0;                       // (same for the tiles)
+    return kPrepHeaderFloats + (((p.wk_per_g * s.G) + 3) & ~(size_t)3);
+}
+
+namespace {
+// one CTA per (unit, group): global -> global transposition into the kernel's table layout
+__global__ void conv_prepare_kernel(const float* __restrict__ w, float* __restrict__ out, size_t w_stride,
+                                    size_t out_stride, Shape s, int transpose, int OB, int OBP, int nob) {
+    const int u = blockIdx.x, g = blockIdx.y;
+    const int C = s.C, KH = s.kH, KW = s.kW;
+    const int per_g = C * C * KH * KW;
+    const float* src = w + (size_t)u * w_stride + (size_t)g * per_g;
+    float* dst = out + (size_t)u * out_stride + kPrepHeaderFloats + (size_t)g * C * KH * KW * nob * OBP;
+    for (int e = threadIdx.x; e < per_g; e += blockDim.x) {
+        int r = e;
+        const int b = r % KW;
+        r /= KW;
+        const int aa = r % KH;
+        r /= KH;
+        const int i = r % C, o = r / C;
+        int cin, cout, ap, bp;
+        if (!transpose) { cin = i; cout = o; ap = aa; bp = b; }
+        else { cin = o; cout = i; ap = KH - 1 - aa; bp = KW - 1 - b; }
+        dst[((((size_t)cin * KH + ap) * KW + bp) * nob + cout / OB) * OBP + cout % OB] = __ldg(src + e);
+    }
+    if (g == 0 && threadIdx.x < 32) {
+        // header: magic, kind, OB, nob, logdet = H*W*sum_g sum_o log|diag corner tap| (forward tables)
+        float ld = 0.f;
+        const float* wu = w + (size_t)u * w_stride;
+        for (int e = threadIdx.x; e < s.G * C; e += 32) {
+            const int gg = e / C, o = e - gg * C;
+            const int ord = order_of(s.orders, gg);
+            ld += logf(fabsf(__ldg(wu + (((size_t)gg * C + o) * C + o) * KH * KW + corner_a(ord, KH) * KW + corner_b(ord, KW))));
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, off);
+        if (threadIdx.x == 0) {
+            float* h = out + (size_t)u * out_stride;
+            h[0] = 1179208259.f; h[1] = (float)transpose; h[2] = (float)OB; h[3] = (float)nob;
+            h[4] = ld * (float)s.H * (float)s.W;
+        }
+    }
+}
+}  // namespace
+
+int launch_conv_prepare(const float* w, float* out, int n_units, size_t w_stride, size_t out_stride, const Shape& s,
+                        bool transpose, cudaStream_t st) {
+    WeightPlan p;
+    if (!plan_weights(s, &p)) return FINC_E_UNSUPPORTED;
+    // padding slots of the table are never read into a stored result: no need to clear them
+    conv_prepare_kernel<<<dim3(n_units, s.G), 256, 0, st>>>(w, out, w_stride, out_stride, s, transpose ? 1 : 0, p.OB, p.OBP, p.nob);
+    return (int)cudaGetLastError();
+}
+
 int launch_conv_fast(const float* x, const float* w, float* y, float* logdet, bool logdet_acc, const Shape& s,
-                     bool transpose, cudaStream_t st, bool* handled) {
+                     bool transpose, bool prepared, cudaStream_t st, bool* handled) {
     *handled = false;
-    if (!(s.kH == s.kW && (s.kH == 3 || s.kH == 5 || s.kH == 2))) return 0;
-    const long tile_floats_l = (long)s.C * s.H * s.W;
-    if (tile_floats_l * 4 > 48 * 1024) return 0;
+    WeightPlan wp;
+    if (!plan_weights(s, &wp)) return 0;
     ConvArgs a{};
     a.x = x; a.w = w; a.y = y; a.logdet = transpose ? nullptr : logdet; a.logdet_acc = logdet_acc ? 1 : 0;
     a.s = s; a.transpose = transpose ? 1 : 0; a.dbg = debug_ts_buffer();
-    a.tile_floats = (int)tile_floats_l;
+    a.tile_floats = s.C * s.H * s.W;
     a.bulk = (a.tile_floats % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     int WT = 1;
     const bool y16 = (reinterpret_cast<uintptr_t>(y) & 15) == 0, y8 = (reinterpret_cast<uintptr_t>(y) & 7) == 0;
     if (s.W % 4 == 0 && y16) WT = 4;  // smem rows are 16-byte aligned because tile_floats % 4 == 0 when W % 4 == 0
     else if (s.W % 2 == 0 && y8 && (a.tile_floats % 2 == 0)) WT = 2;
     a.nstrip = s.W / WT;
-    // channel-count specialisation (3x3 / 5x5, vector strips); everything else is the generic C
-    int ct = 0;
-    if ((s.kH == 3 || s.kH == 5) && WT >= 2)
-        for (int c : {1, 2, 3, 4, 6, 12, 24})
-            if (s.C == c) ct = c;
+    int ct = wp.ct;
+    if (WT < 2) ct = 0;  // (unaligned output: generic-C kernel; same table layout)
+    a.prepared = prepared ? 1 : 0;
+    if (prepared && (!a.bulk || (reinterpret_cast<uintptr_t>(w) & 15) != 0 || conv_prepared_floats(s) == 0)) return FINC_E_UNSUPPORTED;
     const int sms = sm_count_cached();
     const size_t smem_max = max_optin_smem_cached();
     const size_t budget = smem_max > 8192 ? smem_max - 4096 : 0;
-    // group split only when the weights of all groups cannot share the CTA's shared memory
-    a.gsplit = ((size_t)s.G * s.C * s.C * s.kH * s.kW * 4 * 4 / 3 > budget / 2) ? 1 : 0;
+    a.gsplit = wp.gsplit;
     const long n_tiles = a.gsplit ? s.B : (long)s.B * s.G;
     long ctas_max = a.gsplit ? sms / s.G : sms;
     if (ctas_max < 1) ctas_max = 1;
     const long spread = (n_tiles + ctas_max - 1) / ctas_max;
-    const int OB = pick_ob(ct, s.C, (long)s.H * a.nstrip, spread);
-    const int OBP = OB <= 2 ? OB : ((OB + 3) / 4) * 4;
-    a.nob = (s.C + OB - 1) / OB;
-    const size_t wk_per_g = (size_t)s.C * s.kH * s.kW * a.nob * OBP;
-    a.wk_floats = (int)(a.gsplit ? wk_per_g : wk_per_g * s.G);
-    if ((size_t)a.wk_floats * 4 > budget / 2) return 0;
+    const int OB = wp.OB;
+    a.nob = wp.nob;
+    a.wk_floats = (int)(a.gsplit ? wp.wk_per_g : wp.wk_per_g * s.G);
     const int sub_per_tile = a.nob * s.H * a.nstrip;
     if ((long)sub_per_tile >= 65536) return 0;
     a.m_nstrip = magic(a.nstrip); a.m_h = magic(s.H); a.m_nob = magic(a.nob);
@@ -106,7 +188,7 @@ int launch_conv_fast(const float* x, const float* w, float* y, float* logdet, bo
     int cw = (CH * sub_per_tile + 31) / 32;
     if (cw > kMaxConsumerWarps) cw = kMaxConsumerWarps;
     if (cw < 1) cw = 1;
-    const size_t smem = wk_bytes + S * stage_bytes + 32 + 2 * S * 8 + 64;
+    const size_t smem = wk_bytes + S * stage_bytes + 32 + (2 * S + 1) * 8 + 64;
     dim3 grid((unsigned)ctas, a.gsplit ? s.G : 1, 1);
     const int threads = (cw + 1) * 32;
     int rc;
@@ -120,7 +202,7 @@ int launch_conv_fast(const float* x, const float* w, float* y, float* logdet, bo
         case 24: rc = conv::dispatch_ob<24>(OB, WT, s.kH, a, grid, threads, smem, st); break;
         default: rc = conv::dispatch_ob<0>(OB, WT, s.kH, a, grid, threads, smem, st); break;
     }
-    if (rc == FINC_E_UNSUPPORTED) return 0;  // not instantiated: let the generic kernels take it
+    if (rc == FINC_E_UNSUPPORTED) return prepared ? FINC_E_UNSUPPORTED : 0;  // not instantiated: generic kernels
     *handled = true;
     return rc;
 }

@@ -48,6 +48,7 @@ struct ConvArgs {
     int nob;          // output-channel blocks
     int gsplit;       // 1: blockIdx.y selects the group and only its weights are staged
     int bulk;         // 1: TMA bulk copies usable (alignment / size)
+    int prepared;     // 1: a.w is a prepared table [G][wk_per_g] (after the header): one bulk copy
     int tile_floats;  // C*H*W
     int wk_floats;    // weight floats in smem (all groups or one)
     int nstrip;       // W / WT
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kern
     float* bufs = wk + wk_pad + kFrontPad;
     uint64_t* full = reinterpret_cast<uint64_t*>(bufs + (size_t)a.S * stage_floats + 8);  // +8: halo slack behind
     uint64_t* empty = full + a.S;
+    uint64_t* wbar = empty + a.S;  // prepared weight table landed
     const int g_fixed = a.gsplit ? (int)blockIdx.y : -1;
 
     auto chunk_g = [&](long chunk) -> int { return a.gsplit ? g_fixed : (int)(chunk % s.G); };
@@ -242,11 +244,17 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kern
             mbar_init(&full[st], 1);
             mbar_init(&empty[st], nthreads_c >> 5);
         }
+        mbar_init(wbar, 1);
         fence_mbar_init();
     }
     pdl_wait();     // predecessor (producer of x / last writer of y) has completed
     pdl_trigger();  // successor may start its own prologue
     if (a.bulk && is_producer && lane == 0) {
+        if (a.prepared) {  // the whole weight table: one bulk copy
+            const uint32_t wbytes = (uint32_t)a.wk_floats * 4;
+            mbar_arrive_expect_tx(wbar, wbytes);
+            bulk_g2s(wk, a.w + kPrepHeaderFloats + (a.gsplit ? (size_t)g_fixed * a.wk_floats : 0), wbytes, wbar);
+        }
         for (int st = 0; st < a.S; ++st) {
             const long chunk = blockIdx.x + (long)st * gridDim.x;
             if (chunk < a.n_chunks) issue_load(chunk, st);
@@ -259,6 +267,7 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kern
         const int per_g = C * C * kk;
         const int ng = a.gsplit ? 1 : s.G;
         if (threadIdx.x < kFrontPad) wk[wk_pad + threadIdx.x] = 0.f;
+        if (!a.prepared) {
         const float* wsrc = a.w + (a.gsplit ? (long)g_fixed * per_g : 0);
         stage_weights(wsrc, ng * per_g, [&](int e, float v) {
             const int gl = e / per_g;
@@ -273,6 +282,7 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kern
             else { cin = o; cout = i; ap = KH - 1 - aa; bp = KW - 1 - b; }
             wk[((((gl * C + cin) * KH + ap) * KW + bp) * a.nob + cout / OB) * OBP + cout % OB] = v;
         });
+        }
         __syncthreads();
         if (threadIdx.x == 0) dbg_mark(a.dbg, 1);
     }
@@ -280,15 +290,20 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kern
     if (is_producer) {
         // ---- producer warp: keep the ring full; CTA 0 also writes logdet -------------------------
         if (a.logdet != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
-            float ld = 0.f;
-            for (int e = lane; e < s.G * C; e += 32) {
-                const int g = e / C, o = e - g * C;
-                const int ord = order_of(s.orders, g);
-                ld += logf(fabsf(__ldg(a.w + (((long)g * C + o) * C + o) * KH * KW + corner_a(ord, KH) * KW + corner_b(ord, KW))));
-            }
+            float ld;
+            if (a.prepared) {
+                ld = __ldg(a.w + 4);  // computed once by finc_prepare_weights_f32
+            } else {
+                ld = 0.f;
+                for (int e = lane; e < s.G * C; e += 32) {
+                    const int g = e / C, o = e - g * C;
+                    const int ord = order_of(s.orders, g);
+                    ld += logf(fabsf(__ldg(a.w + (((long)g * C + o) * C + o) * KH * KW + corner_a(ord, KH) * KW + corner_b(ord, KW))));
+                }
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, off);
-            ld *= (float)H * (float)W;
+                for (int off = 16; off > 0; off >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, off);
+                ld *= (float)H * (float)W;
+            }
             for (int n = lane; n < s.B; n += 32) a.logdet[n] = a.logdet_acc ? a.logdet[n] + ld : ld;
         }
         if (a.bulk && lane == 0) {
@@ -305,6 +320,7 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kern
     // ---- consumers --------------------------------------------------------------------------------
     const int nob = CT > 0 ? (CT + OB - 1) / OB : a.nob;
     const int sub_per_tile = nob * H * a.nstrip;
+    if (a.prepared) mbar_wait(wbar, 0);
     long k = 0;
     for (long chunk = blockIdx.x; chunk < a.n_chunks; chunk += gridDim.x, ++k) {
         const int st = (int)(k % a.S);

@@ -17,7 +17,73 @@ extern template int dispatch_c<24>(int, int, const WaveArgs&, dim3, int, size_t,
 using wave::WaveArgs;
 using wave::kMaxWarps;
 
-int launch_inverse_wave(const float* z, const float* w, float* x, const Shape& s, cudaStream_t st, bool* handled) {
+namespace {
+struct WavePlan { int CPP, TS, gsplit; size_t wk_per_g; };
+bool plan_wave_weights(const Shape& s, WavePlan* p) {
+    if (!((s.kH == 3 && s.kW == 3) || (s.kH == 5 && s.kW == 5))) return false;
+    const int C = s.C;
+    if (!(C == 1 || C == 2 || C == 3 || C == 4 || C == 6 || C == 12 || C == 24)) return false;
+    if ((long)C * s.H * s.W * 4 > 64 * 1024) return false;
+    p->CPP = C <= 2 ? C : ((C + 3) / 4) * 4;
+    p->TS = (C <= 2) ? C * p->CPP : (((C * p->CPP / 4) % 2 == 1) ? C * p->CPP : C * p->CPP + 4);
+    p->wk_per_g = (size_t)s.kH * s.kW * p->TS;
+    const size_t smem_max = max_optin_smem_cached();
+    const size_t budget = smem_max > 8192 ? smem_max - 4096 : 0;
+    if (p->wk_per_g * s.G * 4 <= budget / 2) p->gsplit = 0;
+    else if (p->wk_per_g * 4 <= budget / 2) p->gsplit = 1;
+    else return false;
+    // parts per pixel must be an instantiated combination (finc_inverse_wave.cuh dispatch_p)
+    int P = 1;
+    while (P < 8 && s.W * (P * 2) <= 32) P *= 2;
+    if (P == 1 && C > 6) return false;
+    if (P == 2 && C > 12) return false;
+    return true;
+}
+
+__global__ void wave_prepare_kernel(const float* __restrict__ w, float* __restrict__ out, size_t w_stride,
+                                    size_t out_stride, Shape s, int CPP, int TS) {
+    const int u = blockIdx.x, g = blockIdx.y;
+    const int C = s.C, KH = s.kH, KW = s.kW;
+    const int per_g = C * C * KH * KW;
+    const float* src = w + (size_t)u * w_stride + (size_t)g * per_g;
+    float* dst = out + (size_t)u * out_stride + kPrepHeaderFloats + (size_t)g * KH * KW * TS;
+    const int ord = order_of(s.orders, g);
+    for (int e = threadIdx.x; e < per_g; e += blockDim.x) {
+        int r = e;
+        const int b = r % KW;
+        r /= KW;
+        const int aa = r % KH;
+        r /= KH;
+        const int i = r % C, o = r / C;
+        const int kh = (ord & 2) ? aa : KH - 1 - aa;
+        const int kw = (ord & 1) ? b : KW - 1 - b;
+        dst[(kh * KW + kw) * TS + i * CPP + o] = __ldg(src + e);
+    }
+    if (g == 0 && threadIdx.x == 0) {
+        float* h = out + (size_t)u * out_stride;
+        h[0] = 1179208259.f; h[1] = 2.f; h[2] = (float)CPP; h[3] = (float)TS;
+    }
+}
+}  // namespace
+
+size_t wave_prepared_floats(const Shape& s) {
+    WavePlan p;
+    if (!plan_wave_weights(s, &p)) return 0;
+    if ((p.gsplit ? p.wk_per_g : p.wk_per_g * s.G) % 4 != 0) return 0;  // bulk copies move 16-byte multiples
+    if (((long)s.C * s.H * s.W) % 4 != 0) return 0;                       // (same for the tiles)
+    return kPrepHeaderFloats + ((p.wk_per_g * s.G + 3) & ~(size_t)3);
+}
+
+int launch_wave_prepare(const float* w, float* out, int n_units, size_t w_stride, size_t out_stride, const Shape& s,
+                        cudaStream_t st) {
+    WavePlan p;
+    if (!plan_wave_weights(s, &p)) return FINC_E_UNSUPPORTED;
+    wave_prepare_kernel<<<dim3(n_units, s.G), 256, 0, st>>>(w, out, w_stride, out_stride, s, p.CPP, p.TS);
+    return (int)cudaGetLastError();
+}
+
+int launch_inverse_wave(const float* z, const float* w, float* x, const Shape& s, bool prepared, cudaStream_t st,
+                        bool* handled) {
     *handled = false;
     if (!((s.kH == 3 && s.kW == 3) || (s.kH == 5 && s.kW == 5))) return 0;
     const int C = s.C;
@@ -25,7 +91,7 @@ int launch_inverse_wave(const float* z, const float* w, float* x, const Shape& s
     const long tile_floats_l = (long)C * s.H * s.W;
     if (tile_floats_l * 4 > 64 * 1024) return 0;
     WaveArgs a{};
-    a.z = z; a.w = w; a.x = x; a.s = s; a.dbg = debug_ts_buffer();
+    a.z = z; a.w = w; a.x = x; a.s = s; a.dbg = debug_ts_buffer(); a.prepared = prepared ? 1 : 0;
     a.tile_floats = (int)tile_floats_l;
     a.tile_stride = (a.tile_floats + 3) & ~3;
     const int CPP = C <= 2 ? C : ((C + 3) / 4) * 4;
@@ -63,7 +129,8 @@ int launch_inverse_wave(const float* z, const float* w, float* x, const Shape& s
     if (nwarps < 1) return 0;
     // a second stage only pays when warps loop over several items and memory is left
     if (items_per_cta > nwarps && (size_t)nwarps * 2 * (stage_bytes + 8) <= avail) a.S = 2;
-    const size_t smem = wk_bytes + (size_t)nwarps * a.S * (stage_bytes + 8) + 16;
+    if (prepared && (!a.bulk || (reinterpret_cast<uintptr_t>(w) & 15) != 0 || wave_prepared_floats(s) == 0)) return FINC_E_UNSUPPORTED;
+    const size_t smem = wk_bytes + (size_t)nwarps * a.S * (stage_bytes + 8) + 8 + 16;
     dim3 grid((unsigned)ctas, a.gsplit ? s.G : 1, 1);
     int rc;
     switch (C) {
@@ -75,7 +142,7 @@ int launch_inverse_wave(const float* z, const float* w, float* x, const Shape& s
         case 12: rc = wave::dispatch_c<12>(s.kH, P, a, grid, nwarps * 32, smem, st); break;
         default: rc = wave::dispatch_c<24>(s.kH, P, a, grid, nwarps * 32, smem, st); break;
     }
-    if (rc == FINC_E_UNSUPPORTED) return 0;  // combination not instantiated: generic tiled kernel
+    if (rc == FINC_E_UNSUPPORTED) return prepared ? FINC_E_UNSUPPORTED : 0;  // combination not instantiated: generic tiled kernel
     *handled = true;
     return rc;
 }

@@ -41,6 +41,7 @@ struct WaveArgs {
     int tile_floats;
     int tile_stride;
     int wk_floats;
+    int prepared;  // 1: a.w is a prepared sweep-ordered table (after the header)
     unsigned long long* dbg;
     long n_items;
 };
@@ -92,12 +93,20 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
 
     if (threadIdx.x == 0) dbg_mark(a.dbg, 0);
     const int n_pre = a.S == 3 ? 2 : a.S;
+    uint64_t* wbar = reinterpret_cast<uint64_t*>(wk + wk_pad + (size_t)nwarps * a.S * stage_floats) + nwarps * a.S;
     if (a.bulk && lane == 0) {
         for (int st = 0; st < a.S; ++st) mbar_init(&bars[st], 1);
+        if (warp == 0) mbar_init(wbar, 1);
         fence_mbar_init();
     }
+    if (a.prepared) __syncthreads();  // wbar initialised before anyone waits on it
     pdl_wait();
     pdl_trigger();
+    if (a.prepared && threadIdx.x == 0) {  // the whole weight table: one bulk copy
+        const uint32_t wbytes = (uint32_t)a.wk_floats * 4;
+        mbar_arrive_expect_tx(wbar, wbytes);
+        bulk_g2s(wk, a.w + kPrepHeaderFloats + (a.gsplit ? (size_t)g_fixed * a.wk_floats : 0), wbytes, wbar);
+    }
     if (a.bulk && lane == 0) {
         for (int st = 0; st < n_pre; ++st) {
             const long item = gw + st * gstride;
@@ -109,6 +118,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
         // (padding lanes o >= C of a row are never read into a stored result)
         constexpr int per_g = C * C * KH * KW;
         const int ng = a.gsplit ? 1 : s.G;
+        if (a.prepared) {
+            mbar_wait(wbar, 0);
+        } else {
         const float* wsrc = a.w + (a.gsplit ? (long)g_fixed * per_g : 0);
         stage_weights(wsrc, ng * per_g, [&](int e, float v) {
             const int gl = e / per_g;
@@ -125,6 +137,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
             wk[((gl * KH + kh) * KW + kw) * TS + i * CPP + o] = v;
         });
         __syncthreads();
+        }
         if (threadIdx.x == 0) dbg_mark(a.dbg, 1);
     }
 

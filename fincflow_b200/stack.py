@@ -150,7 +150,7 @@ class HotPathRunner:
     N_SIDE = 4  # side streams for the mutually independent weight-gradient launches
 
     def __init__(self, stack: FincStack, batch: int, device, slots=1, lr=1e-3, host_io=False,
-                 process_group=None, use_graphs=True):
+                 process_group=None, use_graphs=True, use_prepared=True):
         self.stack, self.B, self.device = stack, batch, torch.device(device)
         self.pg = process_group
         self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)
@@ -166,10 +166,39 @@ class HotPathRunner:
         # (one reduction workspace per stream: calls sharing a workspace must be stream-ordered)
         self.side = [torch.cuda.Stream(self.device) for _ in range(self.N_SIDE)]
         self.workspaces = [_native.new_workspace(ws, self.device) for _ in range(self.N_SIDE)]
+        # prepared weight tables: one batched launch per (level, kind) after every weight update
+        # instead of re-transposing the weights inside each of the 3*n_units launches
+        self.tables = None
+        if use_prepared:
+            tabs = []
+            for lv in stack.levels:
+                nb = [_native.prepared_weights_bytes(kind, batch, 4, lv.cq, lv.height, lv.width, *lv.kernel_size)
+                      for kind in (_native.PREP_FORWARD, _native.PREP_BACKWARD_INPUT, _native.PREP_INVERSE)]
+                if min(nb) == 0:
+                    tabs = None
+                    break
+                tabs.append([torch.empty((lv.n_units, n), dtype=torch.uint8, device=self.device) for n in nb])
+            self.tables = tabs
         self.slots = [_Slot(stack, batch, self.device, host_io) for _ in range(slots)]
         self.graphs = [None] * slots
         self.launches_per_step = None
         self.copy_stream = torch.cuda.Stream(self.device) if host_io else None
+
+    def _prepare_weights(self):
+        if self.tables is None:
+            return
+        st = self.stack
+        for li, lv in enumerate(st.levels):
+            o = st.offsets[li][0]
+            w_units = st.flat.detach()[o:o + lv.n_units * lv.unit_numel].view(lv.n_units, 4 * lv.cq, lv.cq, *lv.kernel_size)
+            for kind in range(3):
+                _native.prepare_weights(w_units, self.tables[li][kind], kind, self.B, lv.height, lv.width)
+
+    def _w(self, li, u, kind):
+        """keyword arguments selecting the raw weights or the prepared table of unit (li, u)"""
+        if self.tables is None:
+            return dict(w=self.stack.unit_weight(li, u).detach())
+        return dict(w=None, prepared=self.tables[li][kind][u], ksize=self.stack.levels[li].kernel_size)
 
     # ---- the four phases as plain launch sequences on the current stream ----------------------
     def _forward(self, s):
@@ -186,8 +215,8 @@ class HotPathRunner:
                 s.acts[li][0].copy_(s.x_host[li], non_blocking=True)
             for u in range(lv.n_units):
                 flags = _native.FLAG_LOGDET_ACCUMULATE if u else 0
-                _native.forward(s.acts[li][u], st.unit_weight(li, u).detach(), flags=flags,
-                                out=s.acts[li][u + 1], logdet_out=s.logdet[li])
+                _native.forward(s.acts[li][u], flags=flags, out=s.acts[li][u + 1], logdet_out=s.logdet[li],
+                                **self._w(li, u, _native.PREP_FORWARD))
             # logp and dz = d(-mean_n logp)/dz = z / (B * world)
             _native.gaussian_logp(s.acts[li][lv.n_units], s.logdet[li], 1.0 / (self.B * self.world),
                                   logp_out=s.logp[li], dz_out=s.dzs[li][lv.n_units])
@@ -215,7 +244,7 @@ class HotPathRunner:
                                             workspace=self.workspaces[k % self.N_SIDE])
                 k += 1
                 if u > 0:
-                    _native.backward_input(s.dzs[li][u + 1], st.unit_weight(li, u).detach(), out=s.dzs[li][u])
+                    _native.backward_input(s.dzs[li][u + 1], out=s.dzs[li][u], **self._w(li, u, _native.PREP_BACKWARD_INPUT))
                     ready = torch.cuda.Event()
                     ready.record(main)
         for side in self.side:
@@ -225,13 +254,14 @@ class HotPathRunner:
         if self.world > 1:
             torch.distributed.all_reduce(self.grad, group=self.pg)  # NCCL over NVLink, training only
         self.opt.step()
+        self._prepare_weights()
 
     def _inverse(self, s):
         st = self.stack
         for li, lv in enumerate(st.levels):
             src, cur = s.zin[li], 0
             for u in reversed(range(lv.n_units)):
-                _native.inverse(src, st.unit_weight(li, u).detach(), out=s.samp[li][cur])
+                _native.inverse(src, out=s.samp[li][cur], **self._w(li, u, _native.PREP_INVERSE))
                 src, cur = s.samp[li][cur], cur ^ 1
             if self.host_io:
                 s.samp_host[li].copy_(src, non_blocking=True)
@@ -245,6 +275,7 @@ class HotPathRunner:
     def prepare(self):
         """warm up eagerly (binds the device, sets kernel attributes, initialises Adam state),
         then capture one CUDA graph per (slot, phase).  The all-reduce stays outside graphs."""
+        self._prepare_weights()
         for s in self.slots:
             for fn in self._phase_fns():
                 fn(s)

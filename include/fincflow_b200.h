@@ -50,6 +50,7 @@ extern "C" {
 #define FINC_FLAG_ACCUMULATE 4u   /* backward_weight: dw += result instead of dw = result */
 #define FINC_FLAG_GENERIC_TILED 16u /* inverse: skip the shape-specialised kernel, use the generic tiled one (testing) */
 #define FINC_FLAG_WORKSPACE_CLEAN 32u /* backward_weight: the first 4 KiB of `workspace` are zero (as every call leaves them) */
+#define FINC_FLAG_PREPARED 64u /* forward / backward_input / inverse: `w` is a table made by finc_prepare_weights_f32 */
 #define FINC_FLAG_LOGDET_ACCUMULATE 8u /* forward: logdet[n] += ... (FlowSequential's `logdet += layer_logdet`) */
 
 /* error codes (negative); positive return values are cudaError_t */
@@ -130,6 +131,27 @@ int finc_logdet_f32(const float* w, float* logdet, int B, int G, int C, int H, i
  * backward of that sum.  z is [B, D] contiguous. */
 int finc_gaussian_logp_f32(const float* z, const float* logdet, float* logp, float* dz, float dz_scale,
                            int B, long D, void* stream);
+
+/* Prepared weight tables (optional fast path for fixed shapes, e.g. CUDA-graph replays).
+ * The tiled kernels need the weights transposed / sweep-ordered in shared memory; by default
+ * every launch re-stages them from the raw [G*C, C, kH, kW] tensor (~1-2 us).  A table prepared
+ * once per weight update is instead fetched with a single TMA bulk copy.
+ *   kind: FINC_PREP_FORWARD | FINC_PREP_BACKWARD_INPUT | FINC_PREP_INVERSE
+ *   finc_prepared_weights_bytes: size of ONE unit's table for this kind and shape, 0 if the shape
+ *     is not covered by the tiled kernels (then FINC_FLAG_PREPARED must not be used).
+ *   finc_prepare_weights_f32: builds `n_units` tables in one launch; unit u reads
+ *     w + u*w_stride_floats and writes prepared + u*prepared_stride_bytes.
+ * A table is valid for exactly the (kind, B, G, C, H, W, kH, kW, orders) it was prepared for and
+ * until the weights change.  Pass it as `w` together with FINC_FLAG_PREPARED (the forward table
+ * carries the unit's logdet, so `logdet` output keeps working). */
+#define FINC_PREP_FORWARD 0
+#define FINC_PREP_BACKWARD_INPUT 1
+#define FINC_PREP_INVERSE 2
+size_t finc_prepared_weights_bytes(int kind, int B, int G, int C, int H, int W, int kH, int kW);
+int finc_prepare_weights_f32(const float* w, void* prepared, int kind, int n_units,
+                             size_t w_stride_floats, size_t prepared_stride_bytes,
+                             int B, int G, int C, int H, int W, int kH, int kW,
+                             unsigned orders, void* stream);
 
 /* Debug aid, inactive unless the environment has FINC_DEBUG_TS=1: the tiled kernels then record
  * per-CTA %globaltimer marks (8 slots per CTA); this call synchronises the device and copies them. */

@@ -306,3 +306,35 @@ def test_reference_pybind_call_site_runs_on_the_shim(nat):
     kern = torch.flip(conv.conv.weight.data, [2, 3]).contiguous()
     yc = compat.cinc_cuda_level1.inverse(torch.flip(zc.detach(), [2, 3]).contiguous(), kern, torch.zeros_like(xc))[0]
     assert (torch.flip(yc, [2, 3]) - xc).abs().max().item() <= RT_TOL
+
+
+@pytest.mark.parametrize("shape", [(256, 12, 16, 16, 3), (256, 24, 8, 8, 3), (256, 48, 4, 4, 3), (37, 12, 32, 32, 3),
+                                   (64, 96, 4, 4, 5), (16, 4, 14, 14, 3)],
+                         ids=lambda s: "B{}C{}_{}x{}_k{}".format(*s))
+def test_prepared_weight_tables_are_bit_identical(nat, shape):
+    """finc_prepare_weights_f32 + FINC_FLAG_PREPARED == staging the raw weights in the kernel"""
+    B, CT, H, W, k = shape
+    torch.manual_seed(5)
+    from fincflow_b200.fastflow import FastFlowUnit
+
+    n_units = 3
+    ws = torch.stack([FastFlowUnit(CT, CT, (k, k)).weight.detach() for _ in range(n_units)]).cuda()
+    ws[1, 0, 0, k - 1, k - 1] = 1.7  # a non-unit diagonal so that logdet is not trivially 0
+    x = torch.randn(B, CT, H, W, device="cuda")
+    for kind, fn in ((nat.PREP_FORWARD, None), (nat.PREP_BACKWARD_INPUT, nat.backward_input), (nat.PREP_INVERSE, nat.inverse)):
+        nb = nat.prepared_weights_bytes(kind, B, 4, CT // 4, H, W, k, k)
+        assert nb > 0 and nb % 128 == 0
+        tables = torch.empty((n_units, nb), dtype=torch.uint8, device="cuda")
+        nat.prepare_weights(ws, tables, kind, B, H, W)
+        for u in range(n_units):
+            if kind == nat.PREP_FORWARD:
+                z0, ld0 = nat.forward(x, ws[u])
+                z1, ld1 = nat.forward(x, None, prepared=tables[u], ksize=(k, k))
+                assert torch.equal(z0, z1)
+                assert torch.allclose(ld0, ld1, rtol=1e-6, atol=1e-6)
+                if u == 1:
+                    assert abs(ld1[0].item() - H * W * np.log(1.7)) <= 1e-3 * H * W
+            else:
+                assert torch.equal(fn(x, ws[u]), fn(x, None, prepared=tables[u], ksize=(k, k)))
+    # shapes outside the tiled kernels report 0 bytes instead of a table
+    assert nat.prepared_weights_bytes(nat.PREP_FORWARD, 4, 1, 5, 6, 6, 2, 3) == 0

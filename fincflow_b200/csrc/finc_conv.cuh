@@ -228,11 +228,12 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kern
 
     auto chunk_g = [&](long chunk) -> int { return a.gsplit ? g_fixed : (int)(chunk % s.G); };
     auto chunk_n0 = [&](long chunk) -> int { return (int)(a.gsplit ? chunk : chunk / s.G) * a.CH; };
-    auto issue_load = [&](long chunk, int st) {  // one elected thread
+    auto issue_load = [&](long chunk, int st) {  // the whole producer warp: copies are issued by 32 lanes
         const int g = chunk_g(chunk), n0 = chunk_n0(chunk);
         const int nt = min(a.CH, s.B - n0);
-        mbar_arrive_expect_tx(&full[st], (uint32_t)(nt * a.tile_floats * 4));
-        for (int t = 0; t < nt; ++t)
+        if (lane == 0) mbar_arrive_expect_tx(&full[st], (uint32_t)(nt * a.tile_floats * 4));
+        __syncwarp();
+        for (int t = lane; t < nt; t += 32)
             bulk_g2s(bufs + (size_t)st * stage_floats + t * a.tile_floats,
                      a.x + ((long)(n0 + t) * s.G + g) * a.tile_floats, (uint32_t)(a.tile_floats * 4), &full[st]);
     };
@@ -249,8 +250,8 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kern
     }
     pdl_wait();     // predecessor (producer of x / last writer of y) has completed
     pdl_trigger();  // successor may start its own prologue
-    if (a.bulk && is_producer && lane == 0) {
-        if (a.prepared) {  // the whole weight table: one bulk copy
+    if (a.bulk && is_producer) {
+        if (a.prepared && lane == 0) {  // the whole weight table: one bulk copy
             const uint32_t wbytes = (uint32_t)a.wk_floats * 4;
             mbar_arrive_expect_tx(wbar, wbytes);
             bulk_g2s(wk, a.w + kPrepHeaderFloats + (a.gsplit ? (size_t)g_fixed * a.wk_floats : 0), wbytes, wbar);
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kern
             }
             for (int n = lane; n < s.B; n += 32) a.logdet[n] = a.logdet_acc ? a.logdet[n] + ld : ld;
         }
-        if (a.bulk && lane == 0) {
+        if (a.bulk) {
             long k = a.S;
             for (long chunk = blockIdx.x + (long)a.S * gridDim.x; chunk < a.n_chunks; chunk += gridDim.x, ++k) {
                 const int st = (int)(k % a.S);

@@ -152,13 +152,14 @@ __global__ void __launch_bounds__((max_consumer_warps(OB, KH) + 1) * 32, 1) wgra
     const bool right = (ord & 1) != 0;
     const int r0 = (ord & 2) ? 0 : -(KH - 1);
 
-    auto issue = [&](int chunk, int st) {  // one elected thread
+    auto issue = [&](int chunk, int st) {  // the whole producer warp: copies are issued by 32 lanes
         const int n0 = chunk * a.CH;
         const int nt = min(a.CH, s.B - n0);
-        mbar_arrive_expect_tx(&full[st], (uint32_t)(2 * nt * a.tile_floats * 4));
+        if (lane == 0) mbar_arrive_expect_tx(&full[st], (uint32_t)(2 * nt * a.tile_floats * 4));
+        __syncwarp();
         float* xs = bufs + (size_t)st * 2 * half;
         float* ds = xs + half;
-        for (int t = 0; t < nt; ++t) {
+        for (int t = lane; t < nt; t += 32) {
             const long off = ((long)(n0 + t) * s.G + g) * a.tile_floats;
             bulk_g2s(xs + t * a.tile_floats, a.x + off, (uint32_t)(a.tile_floats * 4), &full[st]);
             bulk_g2s(ds + t * a.tile_floats, a.dz + off, (uint32_t)(a.tile_floats * 4), &full[st]);
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__((max_consumer_warps(OB, KH) + 1) * 32, 1) wgra
     }
     pdl_wait();
     pdl_trigger();
-    if (a.bulk && is_producer && lane == 0) {
+    if (a.bulk && is_producer) {
         for (int st = 0; st < a.S; ++st) {
             const int chunk = blockIdx.x + st * a.X;
             if (chunk < a.nchunks) issue(chunk, st);
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__((max_consumer_warps(OB, KH) + 1) * 32, 1) wgra
     __syncthreads();
 
     if (is_producer) {
-        if (a.bulk && lane == 0) {
+        if (a.bulk) {
             int k = a.S;
             for (int chunk = blockIdx.x + a.S * a.X; chunk < a.nchunks; chunk += a.X, ++k) {
                 const int st = k % a.S;
@@ -391,90 +392,97 @@ struct Plan {
     size_t smem;
 };
 
+// Plan = (output block OB, combos per CTA / output slices Z, batch slices X, chunk size CH, row
+// ranges RR).  More X = more CTAs sweeping but more partial vectors for the last CTA to sum;
+// more Z = shorter partial vectors but every slice re-reads the tiles.  A small cost model
+// (microseconds, calibrated with tools/kernel_timeline.py) picks the cheapest combination.
 bool make_plan(const Shape& s, Plan* p) {
     if (!(s.kH == s.kW && (s.kH == 3 || s.kH == 5))) return false;
-    if (s.W % 4 == 0) p->WT = 4;
-    else if (s.W % 2 == 0 && s.kW - 1 <= 2) p->WT = 2;  // vector halo needs HALO <= WT
+    int WT;
+    if (s.W % 4 == 0) WT = 4;
+    else if (s.W % 2 == 0 && s.kW - 1 <= 2) WT = 2;  // vector halo needs HALO <= WT
     else return false;
     const long tile_bytes = (long)s.C * s.H * s.W * 4;
     if (tile_bytes > 24 * 1024) return false;
     const int sms = sm_count_cached();
-    p->nstrip = s.W / p->WT;
+    const int nstrip = s.W / WT;
     const int max_ob = s.kH == 3 ? 6 : 2;
     const size_t budget = max_optin_smem_cached() > 8192 ? max_optin_smem_cached() - 4096 : 0;
-    Plan best{};
+    const int kk = s.kH * s.kW;
     bool have = false;
-    // candidates from the most FMA-efficient output block down; keep the first that gives each
-    // SM a few hundred lanes, else the one with the most lanes
-    long best_lanes = -1;
+    double best_cost = 1e30;
+    Plan best{};
     for (int ob : {6, 4, 3, 2, 1}) {
         if (ob > max_ob || ob > s.C) continue;
         if (s.C % ob != 0 && !(ob == 4 && s.C > 6) && ob != 1) continue;
-        Plan q = *p;
-        q.OB = ob;
-        q.nob = (s.C + ob - 1) / ob;
-        q.ncombo = s.C * q.nob;
-        // CTAs per group first assuming Z = 1
-        int xmax = sms / s.G;
-        {
-            const int maxthr0 = max_consumer_warps(ob, s.kH) * 32;
-            const int cpc0 = q.ncombo < maxthr0 ? q.ncombo : maxthr0;  // upper bound of combos per CTA
-            const int xcap0 = 16384 / (cpc0 * ob * s.kH * s.kW);
-            if (xmax > xcap0) xmax = xcap0 < 4 ? 4 : xcap0;
-        }
-        if (xmax < 1) xmax = 1;
-        int CH = (s.B + xmax - 1) / xmax;  // one chunk per CTA when the batch is small
-        const int ch_mem = (int)((budget / 2) / (2 * tile_bytes));  // two tensors, leave half for stages
-        if (CH > ch_mem) CH = ch_mem;
-        if (CH > 16) CH = 16;
-        if (CH < 1) CH = 1;
+        const int nob = (s.C + ob - 1) / ob;
+        const int ncombo = s.C * nob;
+        const int nacc = ob * kk;
         const int maxthr = max_consumer_warps(ob, s.kH) * 32;
-        // row ranges: as many as useful (>= 2 rows each) while the combos still fit one CTA
-        int RR = 1;
-        for (int r : {4, 2, 1}) {
-            if ((s.H + r - 1) / r < 2 && r > 1) continue;
-            RR = r;
-            const int slots = CH * q.nstrip * r;
-            const int SP = slots <= 32 ? (slots <= 1 ? 1 : 1 << (32 - __builtin_clz(slots - 1))) : ((slots + 31) / 32) * 32;
-            if ((long)SP * q.ncombo <= maxthr) break;
+        for (int zt = 1; zt <= ncombo; zt = zt < 4 ? zt + 1 : zt + zt / 2) {
+            Plan q{};
+            q.OB = ob; q.WT = WT; q.nob = nob; q.nstrip = nstrip; q.ncombo = ncombo;
+            q.cpc = (ncombo + zt - 1) / zt;
+            q.Z = (ncombo + q.cpc - 1) / q.cpc;
+            if ((long)s.G * q.Z * 4 > kCounterBytes) continue;
+            if (s.G * q.Z > sms) continue;  // one wave of CTAs
+            int x = sms / (s.G * q.Z);
+            if (x < 1) x = 1;
+            int CH = (s.B + x - 1) / x;  // one chunk per CTA when it fits
+            const long ch_mem = (long)((budget - 16384) / (2 * tile_bytes));
+            if (CH > ch_mem) CH = (int)ch_mem;
+            if (CH > 32) CH = 32;
+            if (CH < 1) CH = 1;
+            // row ranges and slot padding so that the CTA's combos fit its threads
+            int RR = 1, SP = 0;
+            for (;;) {
+                bool ok = false;
+                for (int r : {4, 2, 1}) {
+                    if (r > 1 && (s.H + r - 1) / r < 2) continue;
+                    const int slots = CH * nstrip * r;
+                    const int sp = slots <= 32 ? (slots <= 1 ? 1 : 1 << (32 - __builtin_clz(slots - 1))) : ((slots + 31) / 32) * 32;
+                    if ((long)sp * q.cpc <= maxthr) { RR = r; SP = sp; ok = true; break; }
+                }
+                if (ok || CH == 1) break;
+                CH = CH > 2 ? CH - CH / 4 - (CH < 4 ? 1 : 0) : 1;
+            }
+            if (SP == 0 || (long)SP * q.cpc > maxthr) continue;
+            q.CH = CH; q.RR = RR; q.SP = SP;
+            q.slots = CH * nstrip * RR;
+            q.rpr = (s.H + RR - 1) / RR;
+            q.nchunks = (s.B + CH - 1) / CH;
+            q.X = x < q.nchunks ? x : q.nchunks;
+            const int cpcta = (q.nchunks + q.X - 1) / q.X;
+            q.S = cpcta < 3 ? cpcta : 3;
+            q.threads = ((q.cpc * q.SP + 31) / 32 + 1) * 32;
+            const int nseg = (q.threads - 32) / (q.SP < 32 ? q.SP : 32);
+            for (;;) {
+                q.smem = (size_t)kFrontPad * 4 + (size_t)q.S * 2 * CH * tile_bytes + 32 + (size_t)(nseg * nacc + 2) * 4 +
+                         2 * q.S * 8 + 64;
+                if (q.smem <= budget || q.S == 1) break;
+                --q.S;
+            }
+            if (q.smem > budget) continue;
+            // ---- cost model ----
+            const double warps = (q.threads - 32) / 32.0;
+            const double per_smsp = warps > 4 ? warps / 4 : 1.0;
+            const double row_instr = ob * kk * WT * 1.1 + ob + 6;
+            const double t_sweep = cpcta * (q.rpr + s.kH - 1) * row_instr * per_smsp / 1500.0;
+            int lg = 0;
+            for (int v = 1; v < (SP < 32 ? SP : 32); v <<= 1) ++lg;
+            const double t_reduce = 0.4 + nacc * lg * 2.0 * per_smsp / 1500.0;
+            const double nloc = (double)q.cpc * nacc;
+            const double batches = (nloc * q.X) / ((q.threads) * 8.0);
+            const double t_tail = q.X > 1 ? 1.3 + 0.6 * (batches < 1 ? 1 : batches) : 0.0;
+            const double occupancy_penalty = (double)(s.G * q.Z * q.X) < 0.5 * sms ? 0.5 : 0.0;
+            // first chunk: fixed latency + copy issue (2*CH bulk copies over 32 lanes) + bytes at ~40 KB/us per SM
+            const double t_load = 1.3 + 0.07 * ((2 * CH + 31) / 32) + (2.0 * CH * tile_bytes) / 40000.0;
+            // every output slice re-reads the tiles of its group: Z-fold L2 traffic
+            const double t_traffic = (double)q.Z * 2.0 * s.B * s.G * tile_bytes / 4.0e6;
+            double cost = t_load + t_sweep + t_reduce + t_tail + occupancy_penalty + 0.3 * (cpcta - 1);
+            if (t_traffic > cost) cost = t_traffic;
+            if (cost < best_cost) { best_cost = cost; best = q; have = true; }
         }
-        for (;;) {
-            q.RR = RR;
-            q.slots = CH * q.nstrip * RR;
-            q.SP = q.slots <= 32 ? (q.slots <= 1 ? 1 : 1 << (32 - __builtin_clz(q.slots - 1))) : ((q.slots + 31) / 32) * 32;
-            if (q.SP <= maxthr || CH == 1) break;
-            --CH;
-        }
-        if (q.SP > maxthr) continue;
-        q.CH = CH;
-        q.rpr = (s.H + RR - 1) / RR;
-        q.cpc = maxthr / q.SP;
-        if (q.cpc > q.ncombo) q.cpc = q.ncombo;
-        q.Z = (q.ncombo + q.cpc - 1) / q.cpc;
-        if ((long)s.G * q.Z * 4 > kCounterBytes) continue;
-        q.nchunks = (s.B + CH - 1) / CH;
-        int x = sms / (s.G * q.Z);
-        // the last CTA of a (g,z) slice sums X partial vectors of cpc*NACC floats: keep that tail
-        // to ~one batch of loads per thread
-        const int xcap = 16384 / (q.cpc * ob * s.kH * s.kW);
-        if (x > xcap) x = xcap < 4 ? 4 : xcap;
-        if (x < 1) x = 1;
-        q.X = x < q.nchunks ? x : q.nchunks;
-        const int cpcta = (q.nchunks + q.X - 1) / q.X;
-        q.S = cpcta < 3 ? cpcta : 3;
-        q.threads = ((q.cpc * q.SP + 31) / 32 + 1) * 32;
-        const int nacc = ob * s.kH * s.kW;
-        const int nseg = (q.threads - 32) / (q.SP < 32 ? q.SP : 32);
-        for (;;) {
-            q.smem = (size_t)kFrontPad * 4 + (size_t)q.S * 2 * CH * tile_bytes + 32 + (size_t)(nseg * nacc + 2) * 4 +
-                     2 * q.S * 8 + 64;
-            if (q.smem <= budget || q.S == 1) break;
-            --q.S;
-        }
-        if (q.smem > budget) continue;
-        const long lanes = (long)q.cpc * q.slots;  // busy lanes per CTA
-        if (lanes >= 256) { best = q; have = true; break; }
-        if (lanes > best_lanes) { best = q; best_lanes = lanes; have = true; }
     }
     if (!have) return false;
     *p = best;

@@ -33,6 +33,7 @@ SYMBOLS = (
     "finc_forward_f32", "finc_backward_input_f32", "finc_backward_weight_workspace_bytes",
     "finc_backward_weight_f32", "finc_inverse_f32", "finc_apply_grad_mask_f32", "finc_logdet_f32",
     "finc_gaussian_logp_f32", "finc_debug_timestamps", "finc_prepared_weights_bytes", "finc_prepare_weights_f32",
+    "finc_squeeze_f32", "finc_unsqueeze_f32",
 )
 
 _lib = None
@@ -70,6 +71,10 @@ def load():
     lib.finc_apply_grad_mask_f32.argtypes = [p, i, i, i, i, u, p]
     lib.finc_logdet_f32.argtypes = [p, p, *dims, u, p]
     lib.finc_gaussian_logp_f32.argtypes = [p, p, p, p, ctypes.c_float, i, ctypes.c_long, p]
+    lib.finc_squeeze_f32.restype = i
+    lib.finc_squeeze_f32.argtypes = [p, p, i, i, i, i, p]
+    lib.finc_unsqueeze_f32.restype = i
+    lib.finc_unsqueeze_f32.argtypes = [p, p, i, i, i, i, p]
     lib.finc_prepared_weights_bytes.restype = sz
     lib.finc_prepared_weights_bytes.argtypes = [i] + dims
     lib.finc_prepare_weights_f32.restype = i
@@ -269,6 +274,26 @@ def prepare_weights(w_units, tables, kind, B, H, W, G=4, orders=ORDERS_UNIT):
     _check(load().finc_prepare_weights_f32(w_units.data_ptr(), tables.data_ptr(), kind, n, w_units.stride(0), tables.stride(0),
                                            B, G, C, H, W, kH, kW, orders, _stream(w_units)), "finc_prepare_weights_f32")
     return tables
+
+
+def squeeze(x, out=None):
+    """[B,C,H,W] -> [B,4C,H/2,W/2], channel order 4c + 2dh + dw (layers/squeeze.py:5-13)"""
+    x = _prep(x, "x")
+    _bind_device(x)
+    B, C, H, W = x.shape
+    y = torch.empty((B, 4 * C, H // 2, W // 2), dtype=torch.float32, device=x.device) if out is None else out
+    _check(load().finc_squeeze_f32(x.data_ptr(), y.data_ptr(), B, C, H, W, _stream(x)), "finc_squeeze_f32")
+    return y
+
+
+def unsqueeze(x, out=None):
+    """[B,4C,H,W] -> [B,C,2H,2W] (layers/squeeze.py:16-24)"""
+    x = _prep(x, "x")
+    _bind_device(x)
+    B, C4, H, W = x.shape
+    y = torch.empty((B, C4 // 4, 2 * H, 2 * W), dtype=torch.float32, device=x.device) if out is None else out
+    _check(load().finc_unsqueeze_f32(x.data_ptr(), y.data_ptr(), B, C4, H, W, _stream(x)), "finc_unsqueeze_f32")
+    return y
 
 
 def sm_count() -> int:

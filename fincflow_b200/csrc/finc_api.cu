@@ -203,6 +203,20 @@ int finc_gaussian_logp_f32(const float* z, const float* logdet, float* logp, flo
     return launch_gaussian_logp(z, logdet, logp, dz, dz_scale, B, D, (cudaStream_t)stream);
 }
 
+int finc_squeeze_f32(const float* x, float* y, int B, int C, int H, int W, void* stream) {
+    if (B < 0 || C < 1 || H < 2 || W < 2 || (H & 1) || (W & 1)) return FINC_E_BADARG;
+    if (B == 0) return FINC_OK;
+    if (!x || !y || x == y || (reinterpret_cast<uintptr_t>(x) & 7)) return FINC_E_BADARG;
+    return launch_squeeze(x, y, B, C, H, W, false, (cudaStream_t)stream);
+}
+
+int finc_unsqueeze_f32(const float* x, float* y, int B, int C4, int H, int W, void* stream) {
+    if (B < 0 || C4 < 4 || (C4 & 3) || H < 1 || W < 1) return FINC_E_BADARG;
+    if (B == 0) return FINC_OK;
+    if (!x || !y || x == y || (reinterpret_cast<uintptr_t>(y) & 7)) return FINC_E_BADARG;
+    return launch_squeeze(x, y, B, C4 / 4, 2 * H, 2 * W, true, (cudaStream_t)stream);
+}
+
 size_t finc_prepared_weights_bytes(int kind, int B, int G, int C, int H, int W, int kH, int kW) {
     if (!shape_ok(B, G, C, H, W, kH, kW) || B < 1) return 0;
     const Shape s = mk(B, G, C, H, W, kH, kW, 0);

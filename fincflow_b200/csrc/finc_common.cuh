@@ -195,6 +195,7 @@ int launch_inverse_naive(const float* z, const float* w, float* x, const Shape& 
 int launch_wgrad_naive(const float* dz, const float* x, float* dw, const Shape& s, unsigned flags, cudaStream_t st);
 int launch_mask(float* dw, const Shape& s, cudaStream_t st);
 int launch_logdet(const float* w, float* logdet, bool accumulate, const Shape& s, cudaStream_t st);
+int launch_squeeze(const float* x, float* y, int B, int C, int H, int W, bool inverse, cudaStream_t st);
 int launch_gaussian_logp(const float* z, const float* logdet, float* logp, float* dz, float dz_scale, int B, long D,
                          cudaStream_t st);
 

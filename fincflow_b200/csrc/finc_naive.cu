@@ -194,6 +194,41 @@ int launch_gaussian_logp(const float* z, const float* logdet, float* logp, float
     return (int)cudaGetLastError();
 }
 
+// space-to-depth / depth-to-space (reference layers/squeeze.py:5-24).  One thread per pair of
+// horizontally adjacent un-squeezed pixels: a float2 on the un-squeezed side, two scalars on
+// the squeezed side (lanes run along w on both sides -> coalesced).  C, H, W describe the
+// UN-squeezed tensor [B, C, H, W]; the squeezed one is [B, 4C, H/2, W/2].
+__global__ void squeeze_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int H, int W,
+                               bool inverse) {
+    const int W2 = W >> 1, H2 = H >> 1;
+    const long total = (long)B * C * H * W2;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int j = (int)(e % W2);
+        const int hh = (int)((e / W2) % H);
+        const long nc = e / ((long)W2 * H);  // n*C + c
+        const int c = (int)(nc % C);
+        const long n = nc / C;
+        const long big = (nc * H + hh) * W + 2 * j;                                   // [n][c][hh][2j]
+        const long small0 = (((n * C + c) * 4 + (hh & 1) * 2) * H2 + (hh >> 1)) * W2 + j;  // dw = 0
+        const long small1 = small0 + (long)H2 * W2;                                     // dw = 1
+        if (!inverse) {
+            const float2 v = *reinterpret_cast<const float2*>(src + big);
+            dst[small0] = v.x;
+            dst[small1] = v.y;
+        } else {
+            *reinterpret_cast<float2*>(dst + big) = make_float2(src[small0], src[small1]);
+        }
+    }
+}
+
+int launch_squeeze(const float* x, float* y, int B, int C, int H, int W, bool inverse, cudaStream_t st) {
+    const long total = (long)B * C * H * (W / 2);
+    if (total == 0) return 0;
+    const long blocks = (total + 255) / 256;
+    squeeze_kernel<<<(unsigned)(blocks > 148L * 32 ? 148L * 32 : blocks), 256, 0, st>>>(x, y, B, C, H, W, inverse);
+    return (int)cudaGetLastError();
+}
+
 int launch_conv_naive(const float* x, const float* w, float* y, const Shape& s, bool transpose, cudaStream_t st) {
     const long total = (long)s.B * s.G * s.C * s.H * s.W;
     const int threads = 256;

@@ -1,0 +1,430 @@
+"""Multi-scale FInC flows (MNIST / CIFAR-10 / ImageNet32 / ImageNet64 shapes).
+
+The model definition of the reference's maintained scripts
+(fastflow/fastflow_{mnist,cifar,imagenet,imagenet64}_multi_gpu.py: Preprocess, GlowStep,
+FastFlowStep, FastFlowLevel, FastFlow) rebuilt around the B200 FInC kernels:
+
+  * `FastFlowUnit` and `Squeeze` run on the sm_100a kernels behind the C ABI;
+  * the Glow glue (ActNorm, Conv1x1, Coupling, SplitPrior, preprocessing) stays plain PyTorch
+    ("next" rows) with the reference's formulas
+    (layers/actnorm.py:14-64, conv1x1.py:9-43, coupling.py:9-105, normalize.py:18-31,
+    transforms.py:11-18, dequantize.py:13-19);
+  * the base density is the closed form -0.5|z|^2 - d/2 log(2 pi) on the input's own device
+    instead of a dense d x d MultivariateNormal pinned to cuda:0 (train/losses.py:17-45).
+
+Sub-module and parameter names are the reference's, so its checkpoints load with
+`load_state_dict` (e.g. `fastflow_levels.0.fastflow_level.1.fastflow_step.fastflow_unit.conv_tl.conv.weight`,
+`...glow_unit.glow_step.conv1x1.W`, `...coupling.net.4.logs`).
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _native
+from .fastflow import FastFlowUnit
+from .layers.flowlayer import FlowLayer, PreprocessingFlowLayer
+
+
+# ---------------------------------------------------------------------------------------------
+# glue layers
+# ---------------------------------------------------------------------------------------------
+class _SqueezeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return _native.squeeze(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _native.unsqueeze(g)
+
+
+class _UnsqueezeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return _native.unsqueeze(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _native.squeeze(g)
+
+
+class Squeeze(FlowLayer):
+    """space-to-depth, out channel 4c + 2dh + dw (layers/squeeze.py:5-39) on finc_squeeze_f32"""
+
+    def forward(self, input, context=None):
+        return _SqueezeFn.apply(input), self.logdet(input, context)
+
+    def reverse(self, input, context=None):
+        return _UnsqueezeFn.apply(input)
+
+    def logdet(self, input, context=None):
+        return input.new_zeros(len(input))
+
+
+class Dequantization(PreprocessingFlowLayer):
+    """x + u, u ~ U[0,1) (layers/dequantize.py:13-19).  `fixed_noise` pins u for parity tests
+    (the reference draws it from the CPU generator on every forward)."""
+
+    def __init__(self):
+        super().__init__()
+        self.fixed_noise = None
+
+    def forward(self, input, context=None):
+        u = self.fixed_noise if self.fixed_noise is not None else torch.rand_like(input)
+        return input + u.to(input.device), input.new_zeros(len(input))
+
+    def reverse(self, input, context=None):
+        return input.floor()
+
+    def logdet(self, input, context=None):
+        return input.new_zeros(len(input))
+
+
+class Normalization(PreprocessingFlowLayer):
+    def __init__(self, translation, scale):
+        super().__init__()
+        self.register_buffer("translation", torch.Tensor([translation]))
+        self.register_buffer("scale", torch.Tensor([scale]))
+
+    def forward(self, input, context=None):
+        return (input - self.translation) / self.scale, self.logdet(input, context)
+
+    def reverse(self, input, context=None):
+        return input * self.scale + self.translation
+
+    def logdet(self, input, context=None):
+        N, C, H, W = input.size()
+        return (-C * H * W * torch.log(self.scale)).expand(N)
+
+
+class LogitTransform(PreprocessingFlowLayer):
+    def forward(self, input, context=None):
+        return torch.log(input) - torch.log(1 - input), self.logdet(input, context)
+
+    def reverse(self, input, context=None):
+        return torch.sigmoid(input)
+
+    def logdet(self, input, context=None):
+        return (-torch.log(input) - torch.log(1 - input)).flatten(start_dim=1).sum(-1)
+
+
+class ActNorm(FlowLayer):
+    def __init__(self, n_dims):
+        super().__init__()
+        self.n_dims = n_dims
+        self.translation = nn.Parameter(torch.zeros(n_dims))
+        self.log_scale = nn.Parameter(torch.zeros(n_dims))
+        self.register_buffer("initialized", torch.tensor(0))
+
+    def forward(self, input, context=None):
+        if not self.initialized:  # data-dependent init on the first batch (actnorm.py:17-23)
+            with torch.no_grad():
+                dims = [0, 2, 3]
+                self.translation.data.copy_(input.mean(dim=dims))
+                self.log_scale.data.copy_(torch.log(input.std(dim=dims) + 1e-8))
+                self.initialized.fill_(1)
+        t, ls = self.translation.view(1, -1, 1, 1), self.log_scale.view(1, -1, 1, 1)
+        return (input - t) * torch.exp(-ls), self.logdet(input, context)
+
+    def reverse(self, input, context=None):
+        assert self.initialized
+        t, ls = self.translation.view(1, -1, 1, 1), self.log_scale.view(1, -1, 1, 1)
+        return input * torch.exp(ls) + t
+
+    def logdet(self, input, context=None):
+        H, W = input.shape[2:]
+        return -self.log_scale.sum().expand(input.size(0)) * H * W
+
+
+class Conv1x1(FlowLayer):
+    def __init__(self, n_channels):
+        super().__init__()
+        self.n_channels = n_channels
+        q = torch.linalg.qr(torch.randn(n_channels, n_channels))[0]
+        self.W = nn.Parameter(q.contiguous())
+
+    def forward(self, x, context=None):
+        _, _, H, W = x.size()
+        ldj = H * W * torch.slogdet(self.W)[1]
+        return F.conv2d(x, self.W.view(self.n_channels, self.n_channels, 1, 1)), ldj
+
+    def reverse(self, z, context=None):
+        return F.conv2d(z, torch.inverse(self.W).view(self.n_channels, self.n_channels, 1, 1))
+
+    def logdet(self, input, context=None):
+        return input.shape[2] * input.shape[3] * torch.slogdet(self.W)[1]
+
+
+class Conv2dZero(nn.Module):
+    def __init__(self, in_channels, out_channels, logscale_factor=3):
+        super().__init__()
+        self.logscale_factor = logscale_factor
+        self.weight = nn.Parameter(torch.zeros(out_channels, in_channels, 3, 3))
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+        self.logs = nn.Parameter(torch.zeros(out_channels))
+
+    def forward(self, input):
+        out = F.conv2d(input, self.weight, self.bias, padding=1)
+        return out * torch.exp(self.logs * self.logscale_factor).view(1, -1, 1, 1)
+
+
+class Coupling(FlowLayer):
+    def __init__(self, input_size, width=512):
+        super().__init__()
+        self.n_channels = input_size[0]
+        self.half_channels = self.n_channels // 2
+        self.net = nn.Sequential(nn.Conv2d(self.half_channels, width, 3, padding=1), nn.ReLU(),
+                                 nn.Conv2d(width, width, 1), nn.ReLU(), Conv2dZero(width, self.n_channels))
+
+    def _st(self, x):
+        x1, x2 = x[:, :self.half_channels], x[:, self.half_channels:]
+        h = self.net(x1)
+        log_s = 2.0 * torch.tanh(h[:, ::2] / 2.0)
+        return x1, x2, log_s, h[:, 1::2]
+
+    def forward(self, input, context=None):
+        x1, x2, log_s, t = self._st(input)
+        return torch.cat([x1, x2 * torch.exp(log_s) + t], dim=1), log_s.flatten(start_dim=1).sum(-1)
+
+    def reverse(self, input, context=None):
+        x1, x2, log_s, t = self._st(input)
+        return torch.cat([x1, (x2 - t) * torch.exp(-log_s)], dim=1)
+
+    def logdet(self, input, context=None):
+        return self.forward(input, context)[1]
+
+
+class GaussianPrior(nn.Module):
+    """standard normal over `size`; closed form, device follows the input / `device`"""
+
+    def __init__(self, size):
+        super().__init__()
+        self.size = tuple(size)
+        self.dim = int(math.prod(size))
+        self.register_buffer("_anchor", torch.zeros(()), persistent=False)
+
+    def log_prob(self, input, context=None):
+        return -0.5 * input.reshape(input.shape[0], -1).pow(2).sum(1) - 0.5 * self.dim * math.log(2 * math.pi)
+
+    def forward(self, input, context=None):
+        return -self.log_prob(input, context).sum(-1)
+
+    def sample(self, n_samples, context=None):
+        x = torch.randn(n_samples, *self.size, device=self._anchor.device)
+        return x, self.log_prob(x)
+
+
+class SplitPrior(FlowLayer):
+    """Coupling, then the second half of the channels is modelled by the prior
+    (fastflow_cifar_multi_gpu.py:41-75)"""
+
+    def __init__(self, size, width=512):
+        super().__init__()
+        self.n_channels = size[0]
+        self.transform = Coupling(size, width=width)
+        self.base = GaussianPrior((self.n_channels // 2, size[1], size[2]))
+
+    def forward(self, input, context=None):
+        x, ldj = self.transform(input, context)
+        x1, x2 = x[:, :self.n_channels // 2], x[:, self.n_channels // 2:]
+        return x1, x2, self.base.log_prob(x2) + ldj
+
+    def reverse(self, input, x2=None, context=None):
+        if x2 is None:
+            x2 = torch.randn_like(input)
+        return self.transform.reverse(torch.cat([input, x2], dim=1), context)
+
+    def logdet(self, input, context=None):
+        return self.forward(input, context)[2]
+
+
+# ---------------------------------------------------------------------------------------------
+# flow
+# ---------------------------------------------------------------------------------------------
+class Preprocess(nn.Module):
+    def __init__(self, size):
+        super().__init__()
+        alpha = 1e-6
+        self.layers = nn.Sequential(Dequantization(), Normalization(0, 256),
+                                    Normalization(-alpha, 1 / (1 - 2 * alpha)), LogitTransform())
+
+    def forward(self, x):
+        logdet = 0
+        for layer in self.layers:
+            x, ld = layer(x)
+            logdet = logdet + ld
+        return x, logdet
+
+    def reverse(self, x):
+        for layer in reversed(self.layers):
+            x = layer.reverse(x)
+        return x
+
+
+class _Chain(nn.Module):
+    def _fwd(self, seq, x):
+        logdet = 0
+        for layer in seq:
+            x, ld = layer(x)
+            logdet = logdet + ld
+        return x, logdet
+
+    def _rev(self, seq, x):
+        for layer in reversed(seq):
+            x = layer.reverse(x)
+        return x
+
+
+class GlowStep(_Chain):
+    def __init__(self, size, actnorm=False, width=512):
+        super().__init__()
+        d = OrderedDict()
+        if actnorm:
+            d["actnorm"] = ActNorm(size[0])
+        d["conv1x1"] = Conv1x1(size[0])
+        d["coupling"] = Coupling(size, width)
+        self.glow_step = nn.Sequential(d)
+
+    def forward(self, x):
+        return self._fwd(self.glow_step, x)
+
+    def reverse(self, x):
+        return self._rev(self.glow_step, x)
+
+
+class FastFlowStep(_Chain):
+    def __init__(self, size, actnorm=False, kernel_size=(3, 3), width=512):
+        super().__init__()
+        self.fastflow_step = nn.Sequential(OrderedDict([
+            ("fastflow_unit", FastFlowUnit(size[0], size[0], kernel_size, mask_in_backward=True)),
+            ("glow_unit", GlowStep(size, actnorm, width))]))
+
+    def forward(self, x):
+        return self._fwd(self.fastflow_step, x)
+
+    def reverse(self, x):
+        return self._rev(self.fastflow_step, x)
+
+
+class FastFlowLevel(nn.Module):
+    def __init__(self, size, block_size=16, actnorm=False, kernel_size=(3, 3), width=512):
+        super().__init__()
+        size = (size[0] * 4, size[1] // 2, size[2] // 2)
+        self.fastflow_level = nn.ModuleList([Squeeze(),
+                                             *[FastFlowStep(size, actnorm, kernel_size, width) for _ in range(block_size)],
+                                             SplitPrior(size, width)])
+
+    def forward(self, x):
+        logdet, z = 0, None
+        for layer in self.fastflow_level:
+            if isinstance(layer, SplitPrior):
+                x, z, ld = layer(x)
+            else:
+                x, ld = layer(x)
+            logdet = logdet + ld
+        return x, z, logdet
+
+    def reverse(self, x, z=None):
+        for layer in reversed(self.fastflow_level):
+            x = layer.reverse(x, z) if isinstance(layer, SplitPrior) else layer.reverse(x)
+        return x
+
+
+class FastFlow(nn.Module):
+    """forward(x) -> (zs, logp[B]); reverse(n_samples, zs) -> x; sample(n); reconstruct(x)
+    (fastflow_cifar_multi_gpu.py:295-387).  `final_steps=None` = block_size (CIFAR / ImageNet32
+    scripts); the MNIST and ImageNet64 scripts use ONE final step (`final_steps=1`)."""
+
+    def __init__(self, n_blocks=2, block_size=16, image_size=(1, 28, 28), actnorm=False, kernel_size=(3, 3),
+                 final_steps=None, width=512):
+        super().__init__()
+        C_in, H, W = image_size
+        self.output_size = (C_in * 2 ** (n_blocks + 1), H // 2 ** n_blocks, W // 2 ** n_blocks)
+        self.preprocess = Preprocess(image_size)
+        self.fastflow_levels = nn.ModuleList([
+            FastFlowLevel((C_in * 2 ** i, H // 2 ** i, W // 2 ** i), block_size, actnorm, kernel_size, width)
+            for i in range(n_blocks - 1)])
+        self.squeeze = Squeeze()
+        n_final = block_size if final_steps is None else final_steps
+        self.fastflow_step = nn.Sequential(*[FastFlowStep(self.output_size, actnorm, kernel_size, width)
+                                             for _ in range(n_final)])
+        self.base_distribution = GaussianPrior(self.output_size)
+
+    def forward(self, x, context=None):
+        zs = []
+        x, logdet = self.preprocess(x)
+        for level in self.fastflow_levels:
+            x, z, ld = level(x)
+            logdet = logdet + ld
+            zs.append(z)
+        x, ld = self.squeeze(x)
+        logdet = logdet + ld
+        for step in self.fastflow_step:
+            x, ld = step(x)
+            logdet = logdet + ld
+        zs.append(x)
+        return zs, logdet + self.base_distribution.log_prob(x)
+
+    def reverse(self, n_samples=1, zs=None, z_std=1.0):
+        if zs is None:
+            zs = [self.base_distribution.sample(n_samples)[0]]
+        z = zs[-1]
+        for step in reversed(self.fastflow_step):
+            z = step.reverse(z)
+        x = self.squeeze.reverse(z)
+        for i, level in enumerate(reversed(self.fastflow_levels)):
+            x = level.reverse(x) if len(zs) == 1 else level.reverse(x, zs[-i - 2])
+        return self.preprocess.reverse(x)
+
+    def log_prob(self, x, bits_per_pixel=False):
+        zs, logp = self.forward(x)
+        return logp / (math.log(2) * x[0].numel()) if bits_per_pixel else logp
+
+    def sample(self, n_samples, context=None):
+        x = self.reverse(n_samples=n_samples)
+        return x, x
+
+    def reconstruct(self, x, context=None):
+        zs, _ = self.forward(x)
+        return self.reverse(n_samples=x.shape[0], zs=[zs[-1]])
+
+    def reconstruct_exact(self, x):
+        """true inverse: feeds the split-off latents back (test_layers.py:304-348 reconstruct_ff)"""
+        zs, _ = self.forward(x)
+        return self.reverse(n_samples=x.shape[0], zs=zs)
+
+
+def set_fp32_parity(enabled: bool = True):
+    """The reference ran full fp32 (CUDA 10.2 / cuDNN 7.6 predate TF32).  The glue layers here
+    are PyTorch convolutions whose cuDNN default is TF32 (~5e-4 relative); call this to get the
+    reference's numerics in the glue as well.  The FInC kernels are always fp32 FMA."""
+    torch.backends.cudnn.allow_tf32 = not enabled
+    torch.backends.cuda.matmul.allow_tf32 = not enabled
+
+
+def clear_grad(module):
+    from .fastflow import clear_grad as _cg
+
+    _cg(module)
+
+
+# builders with the reference scripts' settings (SURVEY.md section 8 shape table)
+def fastflow_mnist(**kw):
+    return FastFlow(n_blocks=2, block_size=16, image_size=(1, 28, 28), final_steps=1, **kw)
+
+
+def fastflow_cifar10(**kw):
+    return FastFlow(n_blocks=3, block_size=16, image_size=(3, 32, 32), **kw)
+
+
+def fastflow_imagenet32(**kw):
+    return FastFlow(n_blocks=3, block_size=48, image_size=(3, 32, 32), **kw)
+
+
+def fastflow_imagenet64(kernel_size=(3, 3), **kw):
+    return FastFlow(n_blocks=4, block_size=48, image_size=(3, 64, 64), final_steps=1, kernel_size=kernel_size, **kw)

@@ -132,6 +132,14 @@ int finc_logdet_f32(const float* w, float* logdet, int B, int G, int C, int H, i
 int finc_gaussian_logp_f32(const float* z, const float* logdet, float* logp, float* dz, float dz_scale,
                            int B, long D, void* stream);
 
+/* Squeeze (space-to-depth) and its inverse, the glue between the levels of the multi-scale flow:
+ *   squeeze:   y[n, 4c + 2dh + dw, h, w] = x[n, c, 2h + dh, 2w + dw]      x: [B,C,H,W] -> y: [B,4C,H/2,W/2]
+ *   unsqueeze: the inverse map                                           x: [B,4C,H,W] -> y: [B,C,2H,2W]
+ * Replaces space_to_depth / depth_to_space (layers/squeeze.py:5-24: view + permute + contiguous).
+ * H and W of the un-squeezed tensor must be even.  One HBM round trip, coalesced both ways. */
+int finc_squeeze_f32(const float* x, float* y, int B, int C, int H, int W, void* stream);
+int finc_unsqueeze_f32(const float* x, float* y, int B, int C4, int H, int W, void* stream);
+
 /* Prepared weight tables (optional fast path for fixed shapes, e.g. CUDA-graph replays).
  * The tiled kernels need the weights transposed / sweep-ordered in shared memory; by default
  * every launch re-stages them from the raw [G*C, C, kH, kW] tensor (~1-2 us).  A table prepared

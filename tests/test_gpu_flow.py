@@ -1,0 +1,91 @@
+"""GPU tests of the multi-scale flow assembly (fincflow_b200/flows.py) against a fixture produced
+by the reference's own FastFlow model code (tests/golden/make_golden_flow.py), and of the
+squeeze kernels."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import REPO, rel_err
+
+pytestmark = pytest.mark.gpu
+
+# the glue convolutions are PyTorch/cuDNN: full fp32 like the reference's CUDA 10.2 stack
+# (modern PyTorch defaults cuDNN convs to TF32, ~5e-4 relative)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _ref_space_to_depth(x):  # the formula of layers/squeeze.py:5-13
+    xs = x.size()
+    x = x.view(xs[0], xs[1], xs[2] // 2, 2, xs[3] // 2, 2).permute((0, 1, 3, 5, 2, 4)).contiguous()
+    return x.view(xs[0], xs[1] * 4, xs[2] // 2, xs[3] // 2)
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 32, 32), (5, 1, 28, 28), (2, 12, 16, 16), (1, 6, 2, 2), (256, 3, 32, 32)])
+def test_squeeze_kernels_bit_exact(shape):
+    from fincflow_b200 import _native
+
+    x = torch.randn(*shape, device="cuda")
+    y = _native.squeeze(x)
+    assert torch.equal(y, _ref_space_to_depth(x))
+    assert torch.equal(_native.unsqueeze(y), x)
+    assert _native.squeeze(torch.empty(0, 3, 4, 4, device="cuda")).shape == (0, 12, 2, 2)
+
+
+def test_whole_flow_matches_reference_model():
+    from fincflow_b200.flows import FastFlow, clear_grad
+
+    g = np.load(os.path.join(REPO, "tests", "golden", "flow_golden.npz"))
+    model = FastFlow(n_blocks=3, block_size=2, image_size=(3, 16, 16), actnorm=True, width=16).cuda()
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")}
+    res = model.load_state_dict(sd, strict=False)
+    assert res.missing_keys == []
+    assert set(res.unexpected_keys) <= {"preprocess.layers.0.distribution.empty"}
+    model.preprocess.layers[0].fixed_noise = torch.from_numpy(g["noise"]).cuda()
+    x = torch.from_numpy(g["x"]).cuda()
+    zs, logp = model(x)
+    assert len(zs) == 3 and [tuple(z.shape[1:]) for z in zs] == [(6, 8, 8), (12, 4, 4), (48, 2, 2)]
+    for i, z in enumerate(zs):
+        assert rel_err(z.detach().cpu().numpy(), g[f"zs/{i}"]) <= 1e-4, i
+    assert rel_err(logp.detach().cpu().numpy(), g["logp"]) <= 1e-5
+    # training-step gradients of the FInC weights (mask applied inside the wgrad kernel)
+    (-logp.sum() / x.shape[0]).backward()
+    model.apply(clear_grad)
+    own = {n: p.grad for n, p in model.named_parameters() if n.endswith("fastflow_unit.weight")}
+    assert len(own) == 6
+    for name, grad in own.items():
+        prefix = name[:-len("weight")]
+        want = np.concatenate([g[f"grad/{prefix}conv_{q}.conv.weight"] for q in ("tl", "tr", "bl", "br")], 0)
+        assert rel_err(grad.cpu().numpy(), want) <= 1e-4, name
+        assert np.array_equal(grad.cpu().numpy() == 0, want == 0)
+    # exact reconstruction through the wavefront inverse kernels (pixels are integers)
+    with torch.no_grad():
+        x_rec = model.reverse(n_samples=x.shape[0], zs=[z.detach() for z in zs])
+    assert torch.equal(x_rec, x)
+    assert np.array_equal(x_rec.cpu().numpy(), g["x_rec"])
+
+
+def test_builders_and_sampling_shapes():
+    from fincflow_b200 import flows
+
+    torch.manual_seed(0)
+    m = flows.FastFlow(n_blocks=2, block_size=2, image_size=(1, 28, 28), final_steps=1, width=16).cuda()
+    x = torch.randint(0, 256, (8, 1, 28, 28), device="cuda").float()
+    zs, logp = m(x)
+    assert [tuple(z.shape[1:]) for z in zs] == [(2, 14, 14), (8, 7, 7)] and logp.shape == (8,)
+    assert torch.isfinite(logp).all()
+    with torch.no_grad():
+        s, _ = m.sample(5)
+        assert s.shape == (5, 1, 28, 28)
+        rec = m.reconstruct_exact(x)  # floor(x + u + err): u within err of 0/1 may flip a pixel by one
+        assert (rec - x).abs().max().item() <= 1 and (rec != x).float().mean().item() < 1e-3
+    m64 = flows.FastFlow(n_blocks=4, block_size=1, image_size=(3, 64, 64), final_steps=1, kernel_size=(5, 5),
+                         width=16).cuda()
+    xb = torch.randint(0, 256, (2, 3, 64, 64), device="cuda").float()
+    with torch.no_grad():
+        zs, logp = m64(xb)
+        assert tuple(zs[-1].shape[1:]) == (96, 4, 4)
+        rec = m64.reverse(n_samples=2, zs=zs)
+        assert (rec - xb).abs().max().item() <= 1 and (rec != xb).float().mean().item() < 1e-3

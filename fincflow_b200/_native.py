@@ -25,6 +25,7 @@ FLAG_LOGDET_ACCUMULATE = 8
 FLAG_GENERIC_TILED = 16
 FLAG_WORKSPACE_CLEAN = 32
 FLAG_PREPARED = 64
+FLAG_QUARTER_GPU = 128
 PREP_FORWARD, PREP_BACKWARD_INPUT, PREP_INVERSE = 0, 1, 2
 
 # every symbol declared in include/fincflow_b200.h
@@ -33,7 +34,7 @@ SYMBOLS = (
     "finc_forward_f32", "finc_backward_input_f32", "finc_backward_weight_workspace_bytes",
     "finc_backward_weight_f32", "finc_inverse_f32", "finc_apply_grad_mask_f32", "finc_logdet_f32",
     "finc_gaussian_logp_f32", "finc_debug_timestamps", "finc_prepared_weights_bytes", "finc_prepare_weights_f32",
-    "finc_squeeze_f32", "finc_unsqueeze_f32",
+    "finc_squeeze_f32", "finc_unsqueeze_f32", "finc_adam_step_f32",
 )
 
 _lib = None
@@ -71,6 +72,8 @@ def load():
     lib.finc_apply_grad_mask_f32.argtypes = [p, i, i, i, i, u, p]
     lib.finc_logdet_f32.argtypes = [p, p, *dims, u, p]
     lib.finc_gaussian_logp_f32.argtypes = [p, p, p, p, ctypes.c_float, i, ctypes.c_long, p]
+    lib.finc_adam_step_f32.restype = i
+    lib.finc_adam_step_f32.argtypes = [p, p, p, p, p] + [ctypes.c_float] * 4 + [ctypes.c_long, p]
     lib.finc_squeeze_f32.restype = i
     lib.finc_squeeze_f32.argtypes = [p, p, i, i, i, i, p]
     lib.finc_unsqueeze_f32.restype = i
@@ -274,6 +277,15 @@ def prepare_weights(w_units, tables, kind, B, H, W, G=4, orders=ORDERS_UNIT):
     _check(load().finc_prepare_weights_f32(w_units.data_ptr(), tables.data_ptr(), kind, n, w_units.stride(0), tables.stride(0),
                                            B, G, C, H, W, kH, kW, orders, _stream(w_units)), "finc_prepare_weights_f32")
     return tables
+
+
+def adam_step_(param, grad, exp_avg, exp_avg_sq, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    """in-place Adam on flat fp32 buffers; `step` is a 1-element float device tensor"""
+    _bind_device(param)
+    _check(load().finc_adam_step_f32(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                     step.data_ptr(), lr, betas[0], betas[1], eps, param.numel(), _stream(param)),
+           "finc_adam_step_f32", 2)
+    return param
 
 
 def squeeze(x, out=None):

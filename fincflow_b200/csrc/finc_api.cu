@@ -203,6 +203,13 @@ int finc_gaussian_logp_f32(const float* z, const float* logdet, float* logp, flo
     return launch_gaussian_logp(z, logdet, logp, dz, dz_scale, B, D, (cudaStream_t)stream);
 }
 
+int finc_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* step, float lr,
+                       float beta1, float beta2, float eps, long n, void* stream) {
+    if (n < 0 || (n > 0 && (!param || !grad || !exp_avg || !exp_avg_sq || !step))) return FINC_E_BADARG;
+    if (n == 0) return FINC_OK;
+    return launch_adam(param, grad, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, n, (cudaStream_t)stream);
+}
+
 int finc_squeeze_f32(const float* x, float* y, int B, int C, int H, int W, void* stream) {
     if (B < 0 || C < 1 || H < 2 || W < 2 || (H & 1) || (W & 1)) return FINC_E_BADARG;
     if (B == 0) return FINC_OK;

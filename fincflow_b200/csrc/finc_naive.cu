@@ -229,6 +229,31 @@ int launch_squeeze(const float* x, float* y, int B, int C, int H, int W, bool in
     return (int)cudaGetLastError();
 }
 
+// Adam on a flat buffer; the step counter lives on the device so the launch is graph-replayable.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, float* step, float lr, float b1, float b2, float eps, long n) {
+    const float t = *step + 1.f;
+    const float c1 = 1.f - powf(b1, t), c2 = 1.f - powf(b2, t);
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
+        const float ge = g[e];
+        const float me = b1 * m[e] + (1.f - b1) * ge;
+        const float ve = b2 * v[e] + (1.f - b2) * ge * ge;
+        m[e] = me;
+        v[e] = ve;
+        p[e] -= lr * (me / c1) / (sqrtf(ve / c2) + eps);
+    }
+    // the counter is bumped by a second tiny kernel (adam_tick_kernel) after all blocks have read it
+}
+__global__ void adam_tick_kernel(float* step) { *step += 1.f; }
+
+int launch_adam(float* p, const float* g, float* m, float* v, float* step, float lr, float b1, float b2, float eps,
+                long n, cudaStream_t st) {
+    const long blocks = (n + 255) / 256;
+    adam_kernel<<<(unsigned)(blocks > 148L * 8 ? 148L * 8 : blocks), 256, 0, st>>>(p, g, m, v, step, lr, b1, b2, eps, n);
+    adam_tick_kernel<<<1, 1, 0, st>>>(step);
+    return (int)cudaGetLastError();
+}
+
 int launch_conv_naive(const float* x, const float* w, float* y, const Shape& s, bool transpose, cudaStream_t st) {
     const long total = (long)s.B * s.G * s.C * s.H * s.W;
     const int threads = 256;

@@ -396,7 +396,7 @@ struct Plan {
 // ranges RR).  More X = more CTAs sweeping but more partial vectors for the last CTA to sum;
 // more Z = shorter partial vectors but every slice re-reads the tiles.  A small cost model
 // (microseconds, calibrated with tools/kernel_timeline.py) picks the cheapest combination.
-bool make_plan(const Shape& s, Plan* p) {
+bool make_plan(const Shape& s, Plan* p, int sm_div = 1) {
     if (!(s.kH == s.kW && (s.kH == 3 || s.kH == 5))) return false;
     int WT;
     if (s.W % 4 == 0) WT = 4;
@@ -404,7 +404,8 @@ bool make_plan(const Shape& s, Plan* p) {
     else return false;
     const long tile_bytes = (long)s.C * s.H * s.W * 4;
     if (tile_bytes > 24 * 1024) return false;
-    const int sms = sm_count_cached();
+    int sms = sm_count_cached() / sm_div;  // sm_div > 1: leave room for sibling launches on other streams
+    if (sms < s.G) sms = s.G;
     const int nstrip = s.W / WT;
     const int max_ob = s.kH == 3 ? 6 : 2;
     const size_t budget = max_optin_smem_cached() > 8192 ? max_optin_smem_cached() - 4096 : 0;
@@ -496,16 +497,18 @@ static size_t partial_floats(const Shape& s, const Plan& p) {
 }
 
 size_t wgrad_workspace_floats(const Shape& s) {
-    Plan p{};
-    if (!make_plan(s, &p)) return kCounterBytes / 4;
-    return kCounterBytes / 4 + partial_floats(s, p);
+    Plan p{}, q{};
+    size_t f = 0;
+    if (make_plan(s, &p)) f = partial_floats(s, p);
+    if (make_plan(s, &q, 4)) f = f > partial_floats(s, q) ? f : partial_floats(s, q);
+    return kCounterBytes / 4 + f;
 }
 
 int launch_wgrad_fast(const float* dz, const float* x, float* dw, float* workspace, size_t ws_floats, const Shape& s,
                       unsigned flags, cudaStream_t st, bool* handled) {
     *handled = false;
     Plan p{};
-    if (!make_plan(s, &p)) return 0;
+    if (!make_plan(s, &p, (flags & FINC_FLAG_QUARTER_GPU) ? 4 : 1)) return 0;
     if (ws_floats < kCounterBytes / 4 + partial_floats(s, p)) return FINC_E_WORKSPACE;
     WgArgs a{};
     a.dz = dz; a.x = x; a.dw = dw; a.s = s; a.flags = flags; a.dbg = debug_ts_buffer();

@@ -157,7 +157,11 @@ class HotPathRunner:
         self.host_io, self.use_graphs = host_io, use_graphs
         self.grad = torch.zeros_like(stack.flat.data)
         stack.flat.grad = self.grad
-        self.opt = torch.optim.Adam([stack.flat], lr=lr, capturable=True, foreach=False, fused=True)
+        # Adam state for the flat parameter (one fused launch per step, finc_adam_step_f32)
+        self.lr = lr
+        self.exp_avg = torch.zeros_like(stack.flat.data)
+        self.exp_avg_sq = torch.zeros_like(stack.flat.data)
+        self.adam_step = torch.zeros(1, dtype=torch.float32, device=self.device)
         ws = 16
         for lv in stack.levels:
             ws = max(ws, _native.backward_weight_workspace_bytes(batch, 4, lv.cq, lv.height, lv.width,
@@ -240,7 +244,7 @@ class HotPathRunner:
                 side.wait_event(ready)
                 with torch.cuda.stream(side):
                     _native.backward_weight(s.dzs[li][u + 1], s.acts[li][u], lv.kernel_size,
-                                            out=st.unit_weight(li, u, self.grad),
+                                            out=st.unit_weight(li, u, self.grad), flags=_native.FLAG_QUARTER_GPU,
                                             workspace=self.workspaces[k % self.N_SIDE])
                 k += 1
                 if u > 0:
@@ -253,7 +257,7 @@ class HotPathRunner:
     def _optimizer(self, s):
         if self.world > 1:
             torch.distributed.all_reduce(self.grad, group=self.pg)  # NCCL over NVLink, training only
-        self.opt.step()
+        _native.adam_step_(self.stack.flat.data, self.grad, self.exp_avg, self.exp_avg_sq, self.adam_step, lr=self.lr)
         self._prepare_weights()
 
     def _inverse(self, s):

@@ -51,6 +51,7 @@ extern "C" {
 #define FINC_FLAG_GENERIC_TILED 16u /* inverse: skip the shape-specialised kernel, use the generic tiled one (testing) */
 #define FINC_FLAG_WORKSPACE_CLEAN 32u /* backward_weight: the first 4 KiB of `workspace` are zero (as every call leaves them) */
 #define FINC_FLAG_PREPARED 64u /* forward / backward_input / inverse: `w` is a table made by finc_prepare_weights_f32 */
+#define FINC_FLAG_QUARTER_GPU 128u /* backward_weight: plan for a quarter of the SMs (several independent launches run side by side on different streams) */
 #define FINC_FLAG_LOGDET_ACCUMULATE 8u /* forward: logdet[n] += ... (FlowSequential's `logdet += layer_logdet`) */
 
 /* error codes (negative); positive return values are cudaError_t */
@@ -93,7 +94,7 @@ int finc_backward_input_f32(const float* dz, const float* w, float* dx,
  * (one memset node) unless FINC_FLAG_WORKSPACE_CLEAN promises they are already zero; every
  * successful call leaves them zero, so a workspace zeroed once can be reused with the flag.
  * Calls sharing a workspace must be stream-ordered. */
-size_t finc_backward_weight_workspace_bytes(int B, int G, int C, int H, int W, int kH, int kW);
+size_t finc_backward_weight_workspace_bytes(int B, int G, int C, int H, int W, int kH, int kW);  /* valid for any flags */
 int finc_backward_weight_f32(const float* dz, const float* x, float* dw,
                              void* workspace, size_t workspace_bytes,
                              int B, int G, int C, int H, int W, int kH, int kW,
@@ -131,6 +132,14 @@ int finc_logdet_f32(const float* w, float* logdet, int B, int G, int C, int H, i
  * backward of that sum.  z is [B, D] contiguous. */
 int finc_gaussian_logp_f32(const float* z, const float* logdet, float* logp, float* dz, float dz_scale,
                            int B, long D, void* stream);
+
+/* Adam update of a flat fp32 parameter buffer in one launch (the optimiser step that follows the
+ * masked FInC gradients; reference scripts: torch.optim.Adam, fastflow_imagenet_multi_gpu.py:463):
+ *   m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g;  p -= lr * (m/(1-b1^t)) / (sqrt(v/(1-b2^t)) + eps)
+ * `step` is a device counter (float, incremented by the kernel) so the launch can be replayed
+ * inside a CUDA graph. */
+int finc_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* step,
+                       float lr, float beta1, float beta2, float eps, long n, void* stream);
 
 /* Squeeze (space-to-depth) and its inverse, the glue between the levels of the multi-scale flow:
  *   squeeze:   y[n, 4c + 2dh + dw, h, w] = x[n, c, 2h + dh, 2w + dw]      x: [B,C,H,W] -> y: [B,4C,H/2,W/2]

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
     constexpr int CPP = Pad4<C>::value;
     constexpr int TS = Pad4<C>::tap_stride;
     constexpr int NT = KH * KW - 1;          // non-corner taps
-    constexpr bool CREG = (C <= 6);             // corner weights in registers
+    constexpr bool CREG = (C <= 12);            // corner weights in registers (C(C-1)/2 of them are used)
     constexpr int CB = 32 / P;                  // columns per block
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
 
         // per-item slot tables: shared-memory offset, weight row, register weights
         int noff[NNL], foff[NFLA];
+        int noffi[NNL][SC], foffi[NFLA][SC];  // + i*HW, hoisted out of the step loop
         const float* nwp[NNL];
         const float* fwp[NFLA];
         float wn[WN_REG ? NNL : 1][WN_REG ? SC : 1][WN_REG ? C : 1];
@@ -214,11 +215,13 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
             const bool real = m * P + p < NNEAR;
             noff[m] = (bot ? nkh[m] : -nkh[m]) * W + (right ? nkw[m] : -nkw[m]) + nch[m] * HW;
             nwp[m] = wg + (size_t)((real ? nkh[m] : 0) * KW + nkw[m]) * TS + nch[m] * CPP;
+#pragma unroll
+            for (int i = 0; i < SC; ++i) noffi[m][i] = noff[m] + i * HW;
             if constexpr (WN_REG) {
 #pragma unroll
                 for (int i = 0; i < SC; ++i)
 #pragma unroll
-                    for (int o = 0; o < C; ++o) wn[m][i][o] = real ? nwp[m][i * CPP + o] : 0.f;
+                    for (int o = 0; o < C; ++o) wn[m][i][o] = real ? -nwp[m][i * CPP + o] : 0.f;  // sign folded in
             }
         }
 #pragma unroll
@@ -226,11 +229,13 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
             const bool real = m * P + p < NFAR;
             foff[m] = (bot ? fkh[m] : -fkh[m]) * W + (right ? fkw[m] : -fkw[m]) + fch[m] * HW;
             fwp[m] = wg + (size_t)((real ? fkh[m] : 0) * KW + fkw[m]) * TS + fch[m] * CPP;
+#pragma unroll
+            for (int i = 0; i < SC; ++i) foffi[m][i] = foff[m] + i * HW;
             if constexpr (WF_REG) {
 #pragma unroll
                 for (int i = 0; i < SC; ++i)
 #pragma unroll
-                    for (int o = 0; o < C; ++o) wf[m][i][o] = real ? fwp[m][i * CPP + o] : 0.f;
+                    for (int o = 0; o < C; ++o) wf[m][i][o] = real ? -fwp[m][i * CPP + o] : 0.f;  // sign folded in
             }
         }
         if constexpr (CREG) {
@@ -240,7 +245,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
                 for (int o = 0; o < C; ++o) wc[i][o] = wg[i * CPP + o];
         }
 
-        // acc[o] += xv * w[i][o] (xv already negated) for channel i of a slot
+        // acc[o] -= xv * w[i][o] for channel i of a slot (register weights are stored negated,
+        // shared-memory weights use the negated-multiplicand FMA: no extra instruction either way)
         auto fma_row = [&](float (&acc)[C], float xv, const float* wrow, const float* wreg) {
             if (wreg != nullptr) {
 #pragma unroll
@@ -249,14 +255,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
 #pragma unroll
                 for (int v = 0; v < CPP / 4; ++v) {
                     const float4 f = *reinterpret_cast<const float4*>(wrow + 4 * v);
-                    if (4 * v + 0 < C) acc[4 * v + 0] = fmaf(xv, f.x, acc[4 * v + 0]);
-                    if (4 * v + 1 < C) acc[4 * v + 1] = fmaf(xv, f.y, acc[4 * v + 1]);
-                    if (4 * v + 2 < C) acc[4 * v + 2] = fmaf(xv, f.z, acc[4 * v + 2]);
-                    if (4 * v + 3 < C) acc[4 * v + 3] = fmaf(xv, f.w, acc[4 * v + 3]);
+                    if (4 * v + 0 < C) acc[4 * v + 0] = fmaf(-xv, f.x, acc[4 * v + 0]);
+                    if (4 * v + 1 < C) acc[4 * v + 1] = fmaf(-xv, f.y, acc[4 * v + 1]);
+                    if (4 * v + 2 < C) acc[4 * v + 2] = fmaf(-xv, f.z, acc[4 * v + 2]);
+                    if (4 * v + 3 < C) acc[4 * v + 3] = fmaf(-xv, f.w, acc[4 * v + 3]);
                 }
             } else {
 #pragma unroll
-                for (int o = 0; o < C; ++o) acc[o] = fmaf(xv, wrow[o], acc[o]);
+                for (int o = 0; o < C; ++o) acc[o] = fmaf(-xv, wrow[o], acc[o]);
             }
         };
 
@@ -284,7 +290,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
                 for (int m = 0; m < NNL; ++m) {
                     const bool valid = act_c && hs_c >= nkh[m] && ws >= nkw[m];
 #pragma unroll
-                    for (int i = 0; i < SC; ++i) xa[m][i] = valid ? -base_c[noff[m] + i * HW] : 0.f;
+                    for (int i = 0; i < SC; ++i) xa[m][i] = valid ? base_c[noffi[m][i]] : 0.f;
                 }
                 // (2) loads for the far part of the NEXT pixel (two or more diagonals old)
                 const int rn = step + 1 - jj;
@@ -298,7 +304,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
                 for (int m = 0; m < NFL; ++m) {
                     const bool valid = act_n && hn >= fkh[m] && ws >= fkw[m];
 #pragma unroll
-                    for (int i = 0; i < SC; ++i) xb[m][i] = valid ? -base_n[foff[m] + i * HW] : 0.f;
+                    for (int i = 0; i < SC; ++i) xb[m][i] = valid ? base_n[foffi[m][i]] : 0.f;
                 }
                 // (3) near FMAs, then the P partial sums of the pixel start their shuffle reduction
                 float acc[C];

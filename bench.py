@@ -344,8 +344,7 @@ def main_ours(args):
             "unit": "images/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(elapsed_ms / K, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "units_per_level": UNITS_PER_LEVEL,
-                       "kernel_size": KSIZE, "parallelism": f"dp{world} (batch sharded, NCCL all-reduce of the flat FInC "
-                       "gradient bucket in the train step only; sampling without collective)",
+                       "kernel_size": KSIZE, "parallelism": f"dp{world} (batch sharded; train step: " + ("fused NVLink peer-memory all-reduce + Adam kernel" if getattr(e2e_runner, "fused_collective", False) else "NCCL all-reduce of the flat FInC gradient bucket") + "; sampling without collective)",
                        "l2": f"{NSLOT} rotating input/activation sets (~{NSLOT * 0.2:.1f} GB total, > 126 MB L2); "
                              "intermediates of a step stay L2-resident as in a real flow",
                        "execution": "one CUDA graph per phase (forward, backward = dX chain with the dW launches fanned out over 4 side streams, optimizer, inverse); kernels launched with programmatic dependent launch"},

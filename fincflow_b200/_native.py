@@ -34,7 +34,7 @@ SYMBOLS = (
     "finc_forward_f32", "finc_backward_input_f32", "finc_backward_weight_workspace_bytes",
     "finc_backward_weight_f32", "finc_inverse_f32", "finc_apply_grad_mask_f32", "finc_logdet_f32",
     "finc_gaussian_logp_f32", "finc_debug_timestamps", "finc_prepared_weights_bytes", "finc_prepare_weights_f32",
-    "finc_squeeze_f32", "finc_unsqueeze_f32", "finc_adam_step_f32",
+    "finc_squeeze_f32", "finc_unsqueeze_f32", "finc_adam_step_f32", "finc_allreduce_adam_f32",
 )
 
 _lib = None
@@ -74,6 +74,8 @@ def load():
     lib.finc_gaussian_logp_f32.argtypes = [p, p, p, p, ctypes.c_float, i, ctypes.c_long, p]
     lib.finc_adam_step_f32.restype = i
     lib.finc_adam_step_f32.argtypes = [p, p, p, p, p] + [ctypes.c_float] * 4 + [ctypes.c_long, p]
+    lib.finc_allreduce_adam_f32.restype = i
+    lib.finc_allreduce_adam_f32.argtypes = [p] * 7 + [ctypes.c_float] * 5 + [ctypes.c_long, i, i, p]
     lib.finc_squeeze_f32.restype = i
     lib.finc_squeeze_f32.argtypes = [p, p, i, i, i, i, p]
     lib.finc_unsqueeze_f32.restype = i
@@ -285,6 +287,17 @@ def adam_step_(param, grad, exp_avg, exp_avg_sq, step, lr=1e-3, betas=(0.9, 0.99
     _check(load().finc_adam_step_f32(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
                                      step.data_ptr(), lr, betas[0], betas[1], eps, param.numel(), _stream(param)),
            "finc_adam_step_f32", 2)
+    return param
+
+
+def allreduce_adam_(peer_grad_ptrs_dev, peer_signal_ptrs_dev, local, param, exp_avg, exp_avg_sq, step, rank, world,
+                    lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+    """fused NVLink peer-memory all-reduce(SUM) of the gradient buckets + Adam (finc_allreduce_adam_f32)"""
+    _bind_device(param)
+    _check(load().finc_allreduce_adam_f32(peer_grad_ptrs_dev, peer_signal_ptrs_dev, local.data_ptr(), param.data_ptr(),
+                                          exp_avg.data_ptr(), exp_avg_sq.data_ptr(), step.data_ptr(), lr, betas[0],
+                                          betas[1], eps, grad_scale, param.numel(), rank, world, _stream(param)),
+           "finc_allreduce_adam_f32")
     return param
 
 

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "libfincflow_b200.so")
-SOURCES = ["finc_api.cu", "finc_naive.cu", "finc_conv.cu", "finc_inverse.cu", "finc_inverse_wave.cu", "finc_wgrad.cu"] + [
+SOURCES = ["finc_api.cu", "finc_naive.cu", "finc_conv.cu", "finc_inverse.cu", "finc_inverse_wave.cu", "finc_wgrad.cu", "finc_collective.cu"] + [
     f"finc_inverse_wave_c{c}.cu" for c in (24, 12, 6, 4, 3, 2, 1)] + [  # heaviest first
     f"finc_conv_c{c}.cu" for c in (0, 6, 24, 12, 4, 3, 2, 1)]
 HEADERS = [os.path.join(CSRC, "finc_common.cuh"), os.path.join(CSRC, "finc_inverse_wave.cuh"), os.path.join(CSRC, "finc_conv.cuh"),

@@ -210,6 +210,16 @@ int finc_adam_step_f32(float* param, const float* grad, float* exp_avg, float* e
     return launch_adam(param, grad, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, n, (cudaStream_t)stream);
 }
 
+int finc_allreduce_adam_f32(const void* peer_grad, const void* peer_signal, void* local, float* param, float* exp_avg,
+                            float* exp_avg_sq, float* step, float lr, float beta1, float beta2, float eps,
+                            float grad_scale, long n, int rank, int world, void* stream) {
+    if (!peer_grad || !peer_signal || !local || !param || !exp_avg || !exp_avg_sq || !step || n < 1 || rank < 0 ||
+        rank >= world)
+        return FINC_E_BADARG;
+    return launch_allreduce_adam(peer_grad, peer_signal, local, param, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps,
+                                 grad_scale, n, rank, world, (cudaStream_t)stream);
+}
+
 int finc_squeeze_f32(const float* x, float* y, int B, int C, int H, int W, void* stream) {
     if (B < 0 || C < 1 || H < 2 || W < 2 || (H & 1) || (W & 1)) return FINC_E_BADARG;
     if (B == 0) return FINC_OK;

@@ -198,6 +198,9 @@ int launch_logdet(const float* w, float* logdet, bool accumulate, const Shape& s
 int launch_squeeze(const float* x, float* y, int B, int C, int H, int W, bool inverse, cudaStream_t st);
 int launch_adam(float* p, const float* g, float* m, float* v, float* step, float lr, float b1, float b2, float eps,
                 long n, cudaStream_t st);
+int launch_allreduce_adam(const void* peer_grad, const void* peer_signal, void* local, float* param, float* m, float* v,
+                          float* step, float lr, float b1, float b2, float eps, float grad_scale, long n, int rank,
+                          int world, cudaStream_t st);
 int launch_gaussian_logp(const float* z, const float* logdet, float* logp, float* dz, float dz_scale, int B, long D,
                          cudaStream_t st);
 

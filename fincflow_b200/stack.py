@@ -150,12 +150,15 @@ class HotPathRunner:
     N_SIDE = 4  # side streams for the mutually independent weight-gradient launches
 
     def __init__(self, stack: FincStack, batch: int, device, slots=1, lr=1e-3, host_io=False,
-                 process_group=None, use_graphs=True, use_prepared=True):
+                 process_group=None, use_graphs=True, use_prepared=True, fused_collective=True):
         self.stack, self.B, self.device = stack, batch, torch.device(device)
         self.pg = process_group
         self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)
         self.host_io, self.use_graphs = host_io, use_graphs
         self.grad = torch.zeros_like(stack.flat.data)
+        self.fused_collective = False
+        if self.world > 1 and fused_collective:
+            self._setup_peer_memory()
         stack.flat.grad = self.grad
         # Adam state for the flat parameter (one fused launch per step, finc_adam_step_f32)
         self.lr = lr
@@ -187,6 +190,32 @@ class HotPathRunner:
         self.graphs = [None] * slots
         self.launches_per_step = None
         self.copy_stream = torch.cuda.Stream(self.device) if host_io else None
+
+    def _setup_peer_memory(self):
+        """Put the flat gradient bucket in symmetric (peer-mapped) memory so that the fused
+        all-reduce + Adam kernel can read every rank's bucket over NVLink.  Any failure (no
+        symmetric-memory support, no P2P) leaves the NCCL all-reduce path in place."""
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            n = self.stack.flat.numel()
+            bucket = symm.empty(n, dtype=torch.float32, device=self.device)
+            handle = symm.rendezvous(bucket, self.pg.group_name)
+            if handle.signal_pad_size < 2048:
+                raise RuntimeError("signal pad too small")
+            bucket.zero_()
+            self.rank = torch.distributed.get_rank(self.pg)
+            self.peer_grad = torch.tensor(list(handle.buffer_ptrs), dtype=torch.int64, device=self.device)
+            # our flags live at byte 1024 of the pads, away from the slots torch's own barrier uses
+            self.peer_signal = torch.tensor([p + 1024 for p in handle.signal_pad_ptrs], dtype=torch.int64,
+                                            device=self.device)
+            self.coll_local = torch.zeros(4, dtype=torch.int32, device=self.device)
+            handle.barrier()  # pads and buckets are initialised everywhere before the first step
+            self._symm = (bucket, handle)
+            self.grad = bucket
+            self.fused_collective = True
+        except Exception as e:  # pragma: no cover - depends on the machine
+            self.fused_collective_error = repr(e)
 
     def _prepare_weights(self):
         if self.tables is None:
@@ -255,6 +284,13 @@ class HotPathRunner:
             main.wait_stream(side)
 
     def _optimizer(self, s):
+        if self.fused_collective:
+            # one kernel: cross-rank barrier, P2P reads of every rank's bucket over NVLink, Adam
+            _native.allreduce_adam_(self.peer_grad.data_ptr(), self.peer_signal.data_ptr(), self.coll_local,
+                                    self.stack.flat.data, self.exp_avg, self.exp_avg_sq, self.adam_step,
+                                    self.rank, self.world, lr=self.lr)
+            self._prepare_weights()
+            return
         if self.world > 1:
             torch.distributed.all_reduce(self.grad, group=self.pg)  # NCCL over NVLink, training only
         _native.adam_step_(self.stack.flat.data, self.grad, self.exp_avg, self.exp_avg_sq, self.adam_step, lr=self.lr)
@@ -294,7 +330,7 @@ class HotPathRunner:
         for i, s in enumerate(self.slots):
             gs = []
             for name, fn in zip(self.PHASES, self._phase_fns()):
-                if name == "optimizer" and self.world > 1:
+                if name == "optimizer" and self.world > 1 and not self.fused_collective:
                     gs.append(None)  # eager: NCCL all-reduce + Adam
                     continue
                 g = torch.cuda.CUDAGraph()

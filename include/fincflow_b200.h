@@ -141,6 +141,19 @@ int finc_gaussian_logp_f32(const float* z, const float* logdet, float* logp, flo
 int finc_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* step,
                        float lr, float beta1, float beta2, float eps, long n, void* stream);
 
+/* Fused gradient all-reduce + Adam over NVLink peer memory (multi-GPU training only).
+ * peer_grad / peer_signal: DEVICE arrays of `world` pointers to every rank's gradient bucket and
+ * signal pad (>= 128 bytes each, zero-initialised once) -- symmetric allocations, e.g.
+ * torch.distributed._symmetric_memory (buffer_ptrs_dev / signal_pad_ptrs_dev).  `local` is a
+ * zero-initialised 16-byte device scratch of this rank.  Every rank must launch the call once per
+ * step; the kernel waits for all peers, sums the buckets in rank order (bit-identical parameters
+ * on every rank), scales by grad_scale and applies Adam to this rank's replica.  world <= 16.
+ * Replaces DataParallel's reduce-to-GPU0 + broadcast (fastflow_cifar_multi_gpu.py:439-440). */
+int finc_allreduce_adam_f32(const void* peer_grad, const void* peer_signal, void* local,
+                            float* param, float* exp_avg, float* exp_avg_sq, float* step,
+                            float lr, float beta1, float beta2, float eps, float grad_scale,
+                            long n, int rank, int world, void* stream);
+
 /* Squeeze (space-to-depth) and its inverse, the glue between the levels of the multi-scale flow:
  *   squeeze:   y[n, 4c + 2dh + dw, h, w] = x[n, c, 2h + dh, 2w + dw]      x: [B,C,H,W] -> y: [B,4C,H/2,W/2]
  *   unsqueeze: the inverse map                                           x: [B,4C,H,W] -> y: [B,C,2H,2W]

@@ -110,7 +110,7 @@ int finc_forward_f32(const float* x, const float* w, float* z, float* logdet, in
     bool handled = false;
     const bool prep = (flags & FINC_FLAG_PREPARED) != 0;
     if (prep && (flags & FINC_FLAG_NAIVE)) return FINC_E_BADARG;
-    if (!(flags & FINC_FLAG_NAIVE)) rc = launch_conv_fast(x, w, z, logdet, (flags & FINC_FLAG_LOGDET_ACCUMULATE) != 0, s, false, prep, st, &handled);
+    if (!(flags & FINC_FLAG_NAIVE)) rc = launch_conv_fast(x, w, z, logdet, (flags & FINC_FLAG_LOGDET_ACCUMULATE) != 0, s, false, prep, (flags & FINC_FLAG_HALF_GPU) ? 2 : 1, st, &handled);
     if (rc) return rc;
     if (handled) return FINC_OK;  // logdet was written by the fused epilogue
     if (prep) return FINC_E_UNSUPPORTED;  // the generic kernels need the raw weights
@@ -131,7 +131,7 @@ int finc_backward_input_f32(const float* dz, const float* w, float* dx, int B, i
     bool handled = false;
     const bool prep = (flags & FINC_FLAG_PREPARED) != 0;
     if (prep && (flags & FINC_FLAG_NAIVE)) return FINC_E_BADARG;
-    if (!(flags & FINC_FLAG_NAIVE)) rc = launch_conv_fast(dz, w, dx, nullptr, false, s, true, prep, st, &handled);
+    if (!(flags & FINC_FLAG_NAIVE)) rc = launch_conv_fast(dz, w, dx, nullptr, false, s, true, prep, (flags & FINC_FLAG_HALF_GPU) ? 2 : 1, st, &handled);
     if (rc) return rc;
     if (prep && !handled) return FINC_E_UNSUPPORTED;
     if (!handled) rc = launch_conv_naive(dz, w, dx, s, true, st);

@@ -175,7 +175,7 @@ size_t max_optin_smem_cached();
 
 // launchers implemented by the per-kernel translation units; all return cudaError_t as int
 int launch_conv_fast(const float* x, const float* w, float* y, float* logdet, bool logdet_acc, const Shape& s,
-                     bool transpose, bool prepared, cudaStream_t st, bool* handled);
+                     bool transpose, bool prepared, int sm_div, cudaStream_t st, bool* handled);
 size_t conv_prepared_floats(const Shape& s);
 int launch_conv_prepare(const float* w, float* out, int n_units, size_t w_stride, size_t out_stride, const Shape& s,
                         bool transpose, cudaStream_t st);

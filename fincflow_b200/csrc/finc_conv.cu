@@ -133,7 +133,7 @@ int launch_conv_prepare(const float* w, float* out, int n_units, size_t w_stride
 }
 
 int launch_conv_fast(const float* x, const float* w, float* y, float* logdet, bool logdet_acc, const Shape& s,
-                     bool transpose, bool prepared, cudaStream_t st, bool* handled) {
+                     bool transpose, bool prepared, int sm_div, cudaStream_t st, bool* handled) {
     *handled = false;
     WeightPlan wp;
     if (!plan_weights(s, &wp)) return 0;
@@ -156,7 +156,7 @@ int launch_conv_fast(const float* x, const float* w, float* y, float* logdet, bo
     const size_t budget = smem_max > 8192 ? smem_max - 4096 : 0;
     a.gsplit = wp.gsplit;
     const long n_tiles = a.gsplit ? s.B : (long)s.B * s.G;
-    long ctas_max = a.gsplit ? sms / s.G : sms;
+    long ctas_max = (a.gsplit ? sms / s.G : sms) / (sm_div > 1 ? sm_div : 1);  // (the weight-table layout does not depend on sm_div)
     if (ctas_max < 1) ctas_max = 1;
     const long spread = (n_tiles + ctas_max - 1) / ctas_max;
     const int OB = wp.OB;

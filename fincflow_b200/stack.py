@@ -18,6 +18,7 @@ B200-first choices:
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 
 import torch
@@ -147,7 +148,8 @@ class HotPathRunner:
     """
 
     PHASES = ("forward_logdet", "backward", "optimizer", "inverse")
-    N_SIDE = 4  # side streams for the mutually independent weight-gradient launches
+    # side streams for the mutually independent dW launches (swept 2/3/4/6/8 on B200: 6 is the knee)
+    N_SIDE = int(os.environ.get("FINC_NSIDE", "6"))
 
     def __init__(self, stack: FincStack, batch: int, device, slots=1, lr=1e-3, host_io=False,
                  process_group=None, use_graphs=True, use_prepared=True, fused_collective=True):
@@ -277,7 +279,8 @@ class HotPathRunner:
                                             workspace=self.workspaces[k % self.N_SIDE])
                 k += 1
                 if u > 0:
-                    _native.backward_input(s.dzs[li][u + 1], out=s.dzs[li][u], **self._w(li, u, _native.PREP_BACKWARD_INPUT))
+                    _native.backward_input(s.dzs[li][u + 1], out=s.dzs[li][u],
+                                           **self._w(li, u, _native.PREP_BACKWARD_INPUT))
                     ready = torch.cuda.Event()
                     ready.record(main)
         for side in self.side:

@@ -152,7 +152,7 @@ def main_reference(args):
         "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -166,10 +166,23 @@ def algorithmic_bytes(phase, lv, B):
     return 8 * B * lv.channels * lv.height * lv.width
 
 
+def fp32_peak():
+    """measured FFMA throughput (tools/ffma_peak.cu, recorded in profiles/measured_fp32.json)"""
+    try:
+        with open(os.path.join(REPO, "profiles", "measured_fp32.json")) as f:
+            return float(json.load(f)["fp32_ffma_tflops"])
+    except Exception:
+        return 74.4  # nominal: 148 SMs x 128 lanes x 2 x 1.965 GHz
+
+
 def kernel_detail(torch, _native, dev, peak):
     """each kernel family alone at the three level shapes: batch 256 (the workload) and a
-    batch large enough to stream from HBM; L2 flushed before every timed launch."""
+    batch large enough to stream from HBM; L2 flushed before every timed launch.  The roofline
+    time of a launch is max(algorithmic bytes / HBM peak, flops / fp32 FFMA peak): Cq = 3 is
+    HBM-bound (6.75 flop/B), Cq >= 6 is bound by the fp32 pipe."""
     from fincflow_b200.fastflow import FastFlowUnit
+
+    ffma = fp32_peak()
 
     flush = torch.empty(160 * 1024 * 1024 // 4, device=dev)
     out = []
@@ -189,6 +202,9 @@ def kernel_detail(torch, _native, dev, peak):
                 "inverse": lambda: _native.inverse(x, w, out=y),
             }
             nbytes = 8 * x.numel()
+            flops = 2.0 * B * H * W * CT * (CT // 4) * KSIZE * KSIZE
+            t_roof_us = max(nbytes / peak / 1e3, flops / ffma / 1e6)
+            bound = "hbm" if nbytes / peak / 1e3 >= flops / ffma / 1e6 else "fp32"
             for name, fn in fns.items():
                 for _ in range(3):
                     fn()
@@ -204,7 +220,8 @@ def kernel_detail(torch, _native, dev, peak):
                 us = 1e3 * statistics.median(ts)
                 out.append({"kernel": name, "shape": [B, CT, H, W], "us": round(us, 2),
                             "GBps": round(nbytes / us / 1e3, 1), "frac_of_hbm_peak": round(nbytes / us / 1e3 / peak, 3),
-                            "images_per_s": round(B / us * 1e6)})
+                            "TFLOPs": round(flops / us / 1e6, 2), "bound": bound,
+                            "frac_of_roofline": round(t_roof_us / us, 3), "images_per_s": round(B / us * 1e6)})
             del x, dz, y
     return out
 
@@ -272,7 +289,7 @@ def main_ours(args):
     # ---- e2e: same step through the public API with HOST buffers --------------------------------
     del runner
     torch.cuda.empty_cache()
-    ESLOT = 2
+    ESLOT = 3  # copy-in / compute / copy-out of consecutive steps overlap (HotPathRunner.step)
     e2e_runner = HotPathRunner(stack, B, dev, slots=ESLOT, host_io=True, process_group=pg)
     cpu_gen = torch.Generator().manual_seed(2000 + rank)
     for s in e2e_runner.slots:
@@ -287,6 +304,7 @@ def main_ours(args):
     e0.record()
     for i in range(K):
         e2e_runner.step(i % ESLOT)
+    e2e_runner.drain()  # the timed region ends when the last results have reached the host buffers
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -308,7 +326,7 @@ def main_ours(args):
     # the backward phase overlaps two kernel families on several streams, so only the serial
     # single-family phases give a clean per-launch duration
     kernel_phases = {"forward_logdet": ("finc::conv::conv_cta_kernel (forward)", sum(lv.n_units for lv in lvls)),
-                     "inverse": ("finc::wave::inverse_wave_kernel", sum(lv.n_units for lv in lvls))}
+                     "inverse": ("finc::rw::inverse_rw_kernel", sum(lv.n_units for lv in lvls))}
     pm = dict(zip(HotPathRunner.PHASES, phase_ms))
     dom = max(kernel_phases, key=lambda p: pm[p])
     kname, nlaunch = kernel_phases[dom]
@@ -347,7 +365,7 @@ def main_ours(args):
                        "kernel_size": KSIZE, "parallelism": f"dp{world} (batch sharded; train step: " + ("fused NVLink peer-memory all-reduce + Adam kernel" if getattr(e2e_runner, "fused_collective", False) else "NCCL all-reduce of the flat FInC gradient bucket") + "; sampling without collective)",
                        "l2": f"{NSLOT} rotating input/activation sets (~{NSLOT * 0.2:.1f} GB total, > 126 MB L2); "
                              "intermediates of a step stay L2-resident as in a real flow",
-                       "execution": "one CUDA graph per phase (forward, backward = dX chain with the dW launches fanned out over 4 side streams, optimizer, inverse); kernels launched with programmatic dependent launch"},
+                       "execution": "one CUDA graph per phase (forward, backward = dX chain with the dW launches fanned out over 6 side streams, optimizer, inverse); kernels launched with programmatic dependent launch"},
             "phases_ms": {k: round(v, 4) for k, v in pm.items()},
             "phase_images_per_s": {
                 "forward_logdet": round(B * world / (pm["forward_logdet"] * 1e-3)),
@@ -363,14 +381,32 @@ def main_ours(args):
             "clocks": clocks,
             "kernels": detail,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else any library prints during
+    the run (NCCL's version banner, warnings) was diverted to stderr by main()"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # C-level stdout of this process (and of forked workers) -> stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

@@ -27,6 +27,7 @@ FLAG_WORKSPACE_CLEAN = 32
 FLAG_PREPARED = 64
 FLAG_QUARTER_GPU = 128
 FLAG_HALF_GPU = 256
+FLAG_WAVE_SMEM = 512
 PREP_FORWARD, PREP_BACKWARD_INPUT, PREP_INVERSE = 0, 1, 2
 
 # every symbol declared in include/fincflow_b200.h

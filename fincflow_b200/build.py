@@ -18,10 +18,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "libfincflow_b200.so")
-SOURCES = ["finc_api.cu", "finc_naive.cu", "finc_conv.cu", "finc_inverse.cu", "finc_inverse_wave.cu", "finc_wgrad.cu", "finc_collective.cu"] + [
+SOURCES = [f"finc_inverse_rw_c{c}k{k}.cu" for c, k in ((24, 5), (12, 5), (24, 3), (12, 3), (6, 5), (6, 3), (4, 5), (3, 5), (4, 3),
+                                                      (3, 3), (2, 5), (2, 3), (1, 5), (1, 3))] + [  # heaviest first
+    "finc_api.cu", "finc_naive.cu", "finc_conv.cu", "finc_inverse.cu", "finc_inverse_wave.cu", "finc_inverse_rw.cu",
+    "finc_wgrad.cu", "finc_collective.cu"] + [
     f"finc_inverse_wave_c{c}.cu" for c in (24, 12, 6, 4, 3, 2, 1)] + [  # heaviest first
     f"finc_conv_c{c}.cu" for c in (0, 6, 24, 12, 4, 3, 2, 1)]
-HEADERS = [os.path.join(CSRC, "finc_common.cuh"), os.path.join(CSRC, "finc_inverse_wave.cuh"), os.path.join(CSRC, "finc_conv.cuh"),
+HEADERS = [os.path.join(CSRC, "finc_common.cuh"), os.path.join(CSRC, "finc_inverse_wave.cuh"), os.path.join(CSRC, "finc_inverse_rw.cuh"), os.path.join(CSRC, "finc_conv.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "fincflow_b200.h")]
 
 NVCC_FLAGS = [
@@ -44,6 +47,21 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _deps(src, seen=None):
+    """the source plus every header it includes (transitively, quoted includes only)"""
+    import re
+
+    seen = set() if seen is None else seen
+    src = os.path.normpath(src)
+    if src in seen or not os.path.exists(src):
+        return seen
+    seen.add(src)
+    with open(src) as f:
+        for inc in re.findall(r'^\s*#include\s+"([^"]+)"', f.read(), flags=re.M):
+            _deps(os.path.join(os.path.dirname(src), inc), seen)
+    return seen
+
+
 def _compile(src, obj, verbose):
     cmd = [_nvcc(), *NVCC_FLAGS, "-ccbin", "g++", "-c", src, "-o", obj]
     p = subprocess.run(cmd, capture_output=True, text=True)
@@ -64,7 +82,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         src = os.path.join(CSRC, s)
         obj = os.path.join(OUT_DIR, s.replace(".cu", ".o"))
         objs.append(obj)
-        if force or _stale(obj, [src] + HEADERS):
+        if force or _stale(obj, sorted(_deps(src))):
             jobs.append((src, obj))
     if jobs:
         with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:

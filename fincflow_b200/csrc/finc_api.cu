@@ -172,7 +172,9 @@ int finc_inverse_f32(const float* z, const float* w, float* x, int B, int G, int
     bool handled = false;
     if (!(flags & FINC_FLAG_NAIVE)) {
         const bool prep = (flags & FINC_FLAG_PREPARED) != 0;
-        if (!(flags & FINC_FLAG_GENERIC_TILED)) rc = launch_inverse_wave(z, w, x, s, prep, st, &handled);
+        if (!(flags & (FINC_FLAG_GENERIC_TILED | FINC_FLAG_WAVE_SMEM))) rc = launch_inverse_rw(z, w, x, s, prep, st, &handled);
+        if (rc) return rc;
+        if (!handled && !(flags & FINC_FLAG_GENERIC_TILED)) rc = launch_inverse_wave(z, w, x, s, prep, st, &handled);
         if (rc) return rc;
         if (prep && !handled) return FINC_E_UNSUPPORTED;
         if (!handled) rc = launch_inverse_fast(z, w, x, s, st, &handled);

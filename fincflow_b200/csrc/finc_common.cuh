@@ -182,6 +182,9 @@ int launch_conv_prepare(const float* w, float* out, int n_units, size_t w_stride
 int launch_inverse_fast(const float* z, const float* w, float* x, const Shape& s, cudaStream_t st, bool* handled);
 int launch_inverse_wave(const float* z, const float* w, float* x, const Shape& s, bool prepared, cudaStream_t st,
                         bool* handled);
+int launch_inverse_rw(const float* z, const float* w, float* x, const Shape& s, bool prepared, cudaStream_t st,
+                      bool* handled);
+bool rw_shape_supported(const Shape& s);
 size_t wave_prepared_floats(const Shape& s);
 int launch_wave_prepare(const float* w, float* out, int n_units, size_t w_stride, size_t out_stride, const Shape& s,
                         cudaStream_t st);

@@ -32,11 +32,14 @@ bool plan_wave_weights(const Shape& s, WavePlan* p) {
     if (p->wk_per_g * s.G * 4 <= budget / 2) p->gsplit = 0;
     else if (p->wk_per_g * 4 <= budget / 2) p->gsplit = 1;
     else return false;
-    // parts per pixel must be an instantiated combination (finc_inverse_wave.cuh dispatch_p)
+    return true;
+}
+// parts per pixel must be an instantiated combination (finc_inverse_wave.cuh dispatch_p)
+bool wave_parts_ok(const Shape& s) {
     int P = 1;
     while (P < 8 && s.W * (P * 2) <= 32) P *= 2;
-    if (P == 1 && C > 6) return false;
-    if (P == 2 && C > 12) return false;
+    if (P == 1 && s.C > 6) return false;
+    if (P == 2 && s.C > 12) return false;
     return true;
 }
 
@@ -69,6 +72,7 @@ __global__ void wave_prepare_kernel(const float* __restrict__ w, float* __restri
 size_t wave_prepared_floats(const Shape& s) {
     WavePlan p;
     if (!plan_wave_weights(s, &p)) return 0;
+    if (!wave_parts_ok(s) && !rw_shape_supported(s)) return 0;  // no kernel would take the table
     if ((p.gsplit ? p.wk_per_g : p.wk_per_g * s.G) % 4 != 0) return 0;  // bulk copies move 16-byte multiples
     if (((long)s.C * s.H * s.W) % 4 != 0) return 0;                       // (same for the tiles)
     return kPrepHeaderFloats + ((p.wk_per_g * s.G + 3) & ~(size_t)3);

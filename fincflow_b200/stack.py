@@ -123,6 +123,8 @@ class _Slot:
         f = dict(dtype=torch.float32, device=device)
         self.acts, self.logdet, self.logp, self.dzs, self.samp, self.zin = [], [], [], [], [], []
         self.x_host, self.z_host, self.logp_host, self.samp_host = [], [], [], []
+        self.sample_out = {}
+        self.ev_in, self.ev_computed, self.ev_out = (torch.cuda.Event() for _ in range(3))
         for lv in stack.levels:
             shp = (B, lv.channels, lv.height, lv.width)
             self.acts.append([torch.empty(shp, **f) for _ in range(lv.n_units + 1)])
@@ -191,7 +193,9 @@ class HotPathRunner:
         self.slots = [_Slot(stack, batch, self.device, host_io) for _ in range(slots)]
         self.graphs = [None] * slots
         self.launches_per_step = None
+        self.copy_graphs = [None] * slots
         self.copy_stream = torch.cuda.Stream(self.device) if host_io else None
+        self.copy_out_stream = torch.cuda.Stream(self.device) if host_io else None
 
     def _setup_peer_memory(self):
         """Put the flat gradient bucket in symmetric (peer-mapped) memory so that the fused
@@ -236,18 +240,21 @@ class HotPathRunner:
         return dict(w=None, prepared=self.tables[li][kind][u], ksize=self.stack.levels[li].kernel_size)
 
     # ---- the four phases as plain launch sequences on the current stream ----------------------
+    def _copy_in(self, s):
+        """host -> device: this step's data batch (x) and sampling latents (z) of every level"""
+        for li in range(len(self.stack.levels)):
+            s.acts[li][0].copy_(s.x_host[li], non_blocking=True)
+            s.zin[li].copy_(s.z_host[li], non_blocking=True)
+
+    def _copy_out(self, s):
+        """device -> host: per-sample log-likelihoods and the generated samples of every level"""
+        for li in range(len(self.stack.levels)):
+            s.logp_host[li].copy_(s.logp[li], non_blocking=True)
+            s.samp_host[li].copy_(s.sample_out[li], non_blocking=True)
+
     def _forward(self, s):
         st = self.stack
-        main = torch.cuda.current_stream(self.device)
-        if self.host_io:
-            # latents for the sampling pass travel while the train step computes
-            self.copy_stream.wait_stream(main)
-            with torch.cuda.stream(self.copy_stream):
-                for li in range(len(st.levels)):
-                    s.zin[li].copy_(s.z_host[li], non_blocking=True)
         for li, lv in enumerate(st.levels):
-            if self.host_io:
-                s.acts[li][0].copy_(s.x_host[li], non_blocking=True)
             for u in range(lv.n_units):
                 flags = _native.FLAG_LOGDET_ACCUMULATE if u else 0
                 _native.forward(s.acts[li][u], flags=flags, out=s.acts[li][u + 1], logdet_out=s.logdet[li],
@@ -255,10 +262,6 @@ class HotPathRunner:
             # logp and dz = d(-mean_n logp)/dz = z / (B * world)
             _native.gaussian_logp(s.acts[li][lv.n_units], s.logdet[li], 1.0 / (self.B * self.world),
                                   logp_out=s.logp[li], dz_out=s.dzs[li][lv.n_units])
-            if self.host_io:
-                s.logp_host[li].copy_(s.logp[li], non_blocking=True)
-        if self.host_io:
-            main.wait_stream(self.copy_stream)
 
     def _backward(self, s):
         """dX chain on the current stream; the masked dW of every unit -- written straight into
@@ -306,9 +309,6 @@ class HotPathRunner:
             for u in reversed(range(lv.n_units)):
                 _native.inverse(src, out=s.samp[li][cur], **self._w(li, u, _native.PREP_INVERSE))
                 src, cur = s.samp[li][cur], cur ^ 1
-            if self.host_io:
-                s.samp_host[li].copy_(src, non_blocking=True)
-            s.sample_out = getattr(s, "sample_out", {})
             s.sample_out[li] = src
 
     def _phase_fns(self):
@@ -320,8 +320,12 @@ class HotPathRunner:
         then capture one CUDA graph per (slot, phase).  The all-reduce stays outside graphs."""
         self._prepare_weights()
         for s in self.slots:
+            if self.host_io:
+                self._copy_in(s)
             for fn in self._phase_fns():
                 fn(s)
+            if self.host_io:
+                self._copy_out(s)
         torch.cuda.synchronize(self.device)
         c0 = _native.launch_count
         for fn in self._phase_fns():
@@ -341,6 +345,14 @@ class HotPathRunner:
                     fn(s)
                 gs.append(g)
             self.graphs[i] = gs
+            if self.host_io:
+                cg = {}
+                for which, fn in (("in", self._copy_in), ("out", self._copy_out)):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        fn(s)
+                    cg[which] = g
+                self.copy_graphs[i] = cg
         torch.cuda.synchronize(self.device)
 
     def run_phase(self, slot, phase_idx):
@@ -352,11 +364,52 @@ class HotPathRunner:
             self._phase_fns()[phase_idx](s)
 
     def step(self, slot=0, events=None):
-        """one full hot-path pass; `events` (len(PHASES)+1 torch.cuda.Event) get phase boundaries"""
+        """one full hot-path pass; `events` (len(PHASES)+1 torch.cuda.Event) get phase boundaries.
+
+        With host_io the step is a three-stage pipeline over the slots: host->device copies of
+        this step's inputs (copy-in stream), the four compute phases (current stream) and the
+        device->host copies of its results (copy-out stream) are ordered by events per slot, so
+        the copies of step k+1 / k-1 travel while step k computes.  Results of `slot` are valid on
+        the host after `wait(slot)` (or `drain()`)."""
         n = len(self.PHASES)
+        s = self.slots[slot]
+        main = torch.cuda.current_stream(self.device)
+        if self.host_io:
+            self.copy_stream.wait_event(s.ev_computed)   # previous use of this slot has read its inputs
+            with torch.cuda.stream(self.copy_stream):
+                self._replay_or_run(slot, "in", self._copy_in)
+                s.ev_in.record(self.copy_stream)
+            main.wait_event(s.ev_in)
+            main.wait_event(s.ev_out)                    # previous results of this slot have left the device
         for p in range(n):
             if events is not None:
                 events[p].record()
             self.run_phase(slot, p)
         if events is not None:
             events[n].record()
+        if self.host_io:
+            s.ev_computed.record(main)
+            self.copy_out_stream.wait_event(s.ev_computed)
+            with torch.cuda.stream(self.copy_out_stream):
+                self._replay_or_run(slot, "out", self._copy_out)
+                s.ev_out.record(self.copy_out_stream)
+
+    def _replay_or_run(self, slot, which, fn):
+        g = self.copy_graphs[slot].get(which) if self.copy_graphs[slot] else None
+        if g is not None:
+            g.replay()
+        else:
+            fn(self.slots[slot])
+
+    def wait(self, slot):
+        """block the host until the results of the last step on `slot` are in its pinned buffers"""
+        if self.host_io:
+            self.slots[slot].ev_out.synchronize()
+
+    def drain(self):
+        """make the current stream wait for every outstanding host copy (so that an event recorded
+        after drain() covers the whole pipeline)"""
+        if self.host_io:
+            main = torch.cuda.current_stream(self.device)
+            main.wait_stream(self.copy_stream)
+            main.wait_stream(self.copy_out_stream)

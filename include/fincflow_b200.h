@@ -53,6 +53,7 @@ extern "C" {
 #define FINC_FLAG_PREPARED 64u /* forward / backward_input / inverse: `w` is a table made by finc_prepare_weights_f32 */
 #define FINC_FLAG_QUARTER_GPU 128u /* backward_weight: plan for a quarter of the SMs (several independent launches run side by side on different streams) */
 #define FINC_FLAG_HALF_GPU 256u /* forward / backward_input: use at most half of the SMs (leaves room for concurrent launches on other streams) */
+#define FINC_FLAG_WAVE_SMEM 512u /* inverse: skip the register-window kernel, use the shared-memory wavefront kernel (testing) */
 #define FINC_FLAG_LOGDET_ACCUMULATE 8u /* forward: logdet[n] += ... (FlowSequential's `logdet += layer_logdet`) */
 
 /* error codes (negative); positive return values are cudaError_t */

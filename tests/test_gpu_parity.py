@@ -215,6 +215,44 @@ def test_full_size_properties(nat, shape):
     assert torch.equal(dw, nat.backward_weight(dz, x, (k, k)))
 
 
+INVERSE_KERNEL_CASES = [
+    # (B, CT, H, W, k): every (C, k, P, stacks-per-warp) family of the register-window kernel,
+    # ragged batches (last item has partly empty stacks) and batches deep enough for stacked tiles
+    (256, 12, 16, 16, 3), (256, 24, 8, 8, 3), (256, 48, 4, 4, 3), (1, 48, 4, 4, 3), (7, 24, 8, 8, 3),
+    (3001, 12, 16, 16, 3), (5003, 24, 8, 8, 3), (9001, 48, 4, 4, 3), (20011, 48, 4, 4, 3),
+    (130, 4, 14, 14, 3), (1500, 4, 14, 14, 3), (129, 8, 7, 7, 3), (1027, 8, 7, 7, 3),
+    (33, 12, 32, 32, 3), (67, 16, 6, 10, 3), (64, 96, 4, 4, 3), (1031, 96, 4, 4, 3), (41, 96, 8, 8, 3),
+    (35, 12, 32, 32, 5), (66, 24, 16, 16, 5), (67, 48, 8, 8, 5), (300, 48, 4, 4, 5), (64, 96, 4, 4, 5),
+    (19, 4, 14, 14, 5), (23, 8, 7, 7, 5), (21, 16, 5, 3, 5), (2100, 12, 16, 16, 5),
+]
+
+
+@pytest.mark.parametrize("shape", INVERSE_KERNEL_CASES, ids=lambda s: "B{}C{}_{}x{}_k{}".format(*s))
+def test_inverse_kernel_generations_agree(nat, shape):
+    """register-window kernel (default) == shared-memory wavefront kernel == generic tiled kernel
+    == oracle (on a slice), and inverts the forward at full size"""
+    B, CT, H, W, k = shape
+    torch.manual_seed(B + CT + k)
+    from fincflow_b200.fastflow import FastFlowUnit
+
+    w = FastFlowUnit(CT, CT, (k, k)).weight.detach().cuda()
+    zs = torch.randn(B, CT, H, W, device="cuda")
+    x_rw = nat.inverse(zs, w)
+    x_wave = nat.inverse(zs, w, flags=nat.FLAG_WAVE_SMEM)
+    x_gen = nat.inverse(zs, w, flags=nat.FLAG_GENERIC_TILED)
+    assert rel_err(x_rw.cpu().numpy(), x_wave.cpu().numpy()) <= REL_TOL
+    assert rel_err(x_rw.cpu().numpy(), x_gen.cpu().numpy()) <= REL_TOL
+    assert rel_err(nat.forward(x_rw, w)[0].cpu().numpy(), zs.cpu().numpy()) <= REL_TOL
+    # oracle on the first and last images (the last item is the ragged one)
+    sel = torch.cat([zs[:3], zs[-3:]]) if B > 6 else zs
+    got = torch.cat([x_rw[:3], x_rw[-3:]]) if B > 6 else x_rw
+    assert rel_err(got.cpu().numpy(), fo.inverse(sel.cpu().numpy(), w.cpu().numpy())) <= REL_TOL
+    # in place
+    buf = zs.clone()
+    nat.inverse(buf, w, out=buf)
+    assert torch.equal(buf, x_rw)
+
+
 def test_large_batch_beyond_reference_limit(nat):
     """B > 1024: the reference kernel maps the batch to blockDim.x and cannot launch
     (cinc_cuda_kernel_level2.cu:110-111)."""

@@ -101,6 +101,40 @@ def test_host_io_step_and_adam_update():
         assert (h.cpu() - s.z_host[li]).abs().max().item() <= 1e-4
 
 
+def test_host_io_pipeline_over_slots():
+    """copy-in / compute / copy-out of consecutive steps overlap; every slot still gets the
+    results of ITS inputs (lr = 0 keeps the weights fixed so each step has a closed-form answer)"""
+    from fincflow_b200.stack import FincStack, HotPathRunner
+
+    torch.manual_seed(2)
+    B, NS = 5, 3
+    lv = _small_levels()
+    stack = FincStack(lv).cuda()
+    runner = HotPathRunner(stack, B, "cuda", slots=NS, lr=0.0, host_io=True)
+    for s in runner.slots:
+        for li in range(len(lv)):
+            s.x_host[li].normal_()
+            s.z_host[li].normal_()
+    runner.prepare()
+    for rounds in range(3):
+        for k in range(NS):
+            # fresh inputs for the slot: its previous results must have landed before we overwrite
+            runner.wait(k)
+            for li in range(len(lv)):
+                runner.slots[k].x_host[li].normal_()
+                runner.slots[k].z_host[li].normal_()
+            runner.step(k)
+    runner.drain()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        for s in runner.slots:
+            for li in range(len(lv)):
+                z, logp = stack.forward(s.x_host[li].cuda(), li)
+                assert (logp.cpu() - s.logp_host[li]).abs().max().item() <= 1e-5 * max(1.0, logp.abs().max().item())
+                x = stack.reverse(s.z_host[li].cuda(), li)
+                assert rel_err(x.cpu().numpy(), s.samp_host[li].numpy()) <= 1e-5
+
+
 def test_reference_cpu_path_twin_agrees():
     """bench.py's reference arm computes the same step as the GPU runner"""
     from fincflow_b200.stack import FincStack, HotPathRunner, LevelSpec

@@ -23,6 +23,9 @@
 //     floating-point atomics anywhere.
 #include "finc_common.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace finc {
 
 namespace {
@@ -413,7 +416,11 @@ bool make_plan(const Shape& s, Plan* p, int sm_div = 1) {
     bool have = false;
     double best_cost = 1e30;
     Plan best{};
+    // FINC_WG_FORCE="ob,z,ch" pins parts of the plan (0 = free): used by tools/sweep_wgrad.py
+    int f_ob = 0, f_z = 0, f_ch = 0;
+    if (const char* e = getenv("FINC_WG_FORCE")) sscanf(e, "%d,%d,%d", &f_ob, &f_z, &f_ch);
     for (int ob : {6, 4, 3, 2, 1}) {
+        if (f_ob && ob != f_ob) continue;
         if (ob > max_ob || ob > s.C) continue;
         if (s.C % ob != 0 && !(ob == 4 && s.C > 6) && ob != 1) continue;
         const int nob = (s.C + ob - 1) / ob;
@@ -425,6 +432,7 @@ bool make_plan(const Shape& s, Plan* p, int sm_div = 1) {
             q.OB = ob; q.WT = WT; q.nob = nob; q.nstrip = nstrip; q.ncombo = ncombo;
             q.cpc = (ncombo + zt - 1) / zt;
             q.Z = (ncombo + q.cpc - 1) / q.cpc;
+            if (f_z && q.Z != f_z) continue;
             if ((long)s.G * q.Z * 4 > kCounterBytes) continue;
             if (s.G * q.Z > sms) continue;  // one wave of CTAs
             int x = sms / (s.G * q.Z);
@@ -433,6 +441,7 @@ bool make_plan(const Shape& s, Plan* p, int sm_div = 1) {
             const long ch_mem = (long)((budget - 16384) / (2 * tile_bytes));
             if (CH > ch_mem) CH = (int)ch_mem;
             if (CH > 32) CH = 32;
+            if (f_ch && CH > f_ch) CH = f_ch;
             if (CH < 1) CH = 1;
             // row ranges and slot padding so that the CTA's combos fit its threads
             int RR = 1, SP = 0;
@@ -464,23 +473,26 @@ bool make_plan(const Shape& s, Plan* p, int sm_div = 1) {
                 --q.S;
             }
             if (q.smem > budget) continue;
-            // ---- cost model ----
+            // ---- cost model (microseconds; constants fitted to tools/sweep_wgrad.py on B200) ----
             const double warps = (q.threads - 32) / 32.0;
             const double per_smsp = warps > 4 ? warps / 4 : 1.0;
-            const double row_instr = ob * kk * WT * 1.1 + ob + 6;
-            const double t_sweep = cpcta * (q.rpr + s.kH - 1) * row_instr * per_smsp / 1500.0;
+            const double row_instr = ob * kk * WT + 4 * ob + 20;  // FMAs + strip loads + per-row bookkeeping
+            const double t_sweep = cpcta * (q.rpr + s.kH - 1) * row_instr * per_smsp / 1200.0;
             int lg = 0;
             for (int v = 1; v < (SP < 32 ? SP : 32); v <<= 1) ++lg;
-            const double t_reduce = 0.4 + nacc * lg * 2.0 * per_smsp / 1500.0;
+            const double t_reduce = 0.4 + nacc * lg * 2.0 * per_smsp / 1200.0;
             const double nloc = (double)q.cpc * nacc;
             const double batches = (nloc * q.X) / ((q.threads) * 8.0);
             const double t_tail = q.X > 1 ? 1.3 + 0.6 * (batches < 1 ? 1 : batches) : 0.0;
             const double occupancy_penalty = (double)(s.G * q.Z * q.X) < 0.5 * sms ? 0.5 : 0.0;
-            // first chunk: fixed latency + copy issue (2*CH bulk copies over 32 lanes) + bytes at ~40 KB/us per SM
-            const double t_load = 1.3 + 0.07 * ((2 * CH + 31) / 32) + (2.0 * CH * tile_bytes) / 40000.0;
+            // a chunk: copy issue (2*CH bulk copies over 32 lanes) + bytes at ~40 KB/us per SM; the first
+            // one is exposed, the others overlap the sweep but bound it from below
+            const double t_chunk = 0.07 * ((2 * CH + 31) / 32) + (2.0 * CH * tile_bytes) / 40000.0;
+            const double t_ingest = (cpcta - 1) * t_chunk;
             // every output slice re-reads the tiles of its group: Z-fold L2 traffic
             const double t_traffic = (double)q.Z * 2.0 * s.B * s.G * tile_bytes / 4.0e6;
-            double cost = t_load + t_sweep + t_reduce + t_tail + occupancy_penalty + 0.3 * (cpcta - 1);
+            double cost = 1.3 + t_chunk + (t_sweep > t_ingest ? t_sweep : t_ingest) + t_reduce + t_tail + occupancy_penalty +
+                          1.5 * (cpcta - 1);
             if (t_traffic > cost) cost = t_traffic;
             if (cost < best_cost) { best_cost = cost; best = q; have = true; }
         }
@@ -510,6 +522,13 @@ int launch_wgrad_fast(const float* dz, const float* x, float* dw, float* workspa
     Plan p{};
     if (!make_plan(s, &p, (flags & FINC_FLAG_QUARTER_GPU) ? 4 : 1)) return 0;
     if (ws_floats < kCounterBytes / 4 + partial_floats(s, p)) return FINC_E_WORKSPACE;
+    {
+        static const bool dbg_plan = getenv("FINC_WG_DEBUG") != nullptr;
+        if (dbg_plan)
+            fprintf(stderr, "wgrad plan B%d G%d C%d %dx%d k%d: OB=%d WT=%d nob=%d nstrip=%d RR=%d rpr=%d slots=%d SP=%d ncombo=%d cpc=%d Z=%d X=%d CH=%d S=%d nchunks=%d threads=%d smem=%zu\n",
+                    s.B, s.G, s.C, s.H, s.W, s.kH, p.OB, p.WT, p.nob, p.nstrip, p.RR, p.rpr, p.slots, p.SP, p.ncombo, p.cpc,
+                    p.Z, p.X, p.CH, p.S, p.nchunks, p.threads, p.smem);
+    }
     WgArgs a{};
     a.dz = dz; a.x = x; a.dw = dw; a.s = s; a.flags = flags; a.dbg = debug_ts_buffer();
     a.counters = reinterpret_cast<unsigned*>(workspace);

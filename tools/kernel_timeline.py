@@ -20,7 +20,7 @@ for (CT, H, W) in ((12, 16, 16), (24, 8, 8), (48, 4, 4)):
     ws = _native.new_workspace(_native.backward_weight_workspace_bytes(B, 4, CT // 4, H, W, 3, 3), dev)
     fns = {"forward": lambda: _native.forward(x, w, out=y, want_logdet=False),
            "inverse": lambda: _native.inverse(x, w, out=y),
-           "backward_weight": lambda: _native.backward_weight(dz, x, (3, 3), out=dw, workspace=ws)}
+           "backward_weight": lambda: _native.backward_weight(dz, x, (3, 3), out=dw, workspace=ws, flags=int(os.environ.get("FINC_TL_DWFLAGS", "0")))}
     for name, fn in fns.items():
         for _ in range(3):
             fn()

@@ -37,6 +37,27 @@ def launches(src, dst):
                     f"{g('smsp__inst_executed.sum')} | {g('smsp__issue_active.avg.pct_of_peak_sustained_active')} |\n")
 
 
+def shares(src, dst, title=""):
+    """aggregate a launch list per kernel: launches, total/avg duration, share of the total"""
+    lines = [l for l in open(src) if not l.startswith("==")]
+    tot = defaultdict(lambda: [0, 0.0])
+    for row in csv.DictReader(lines):
+        if row["Metric Name"] != "gpu__time_duration.sum":
+            continue
+        v = float(row["Metric Value"].replace(",", ""))
+        v = v / 1e3 if row["Metric Unit"].startswith("ns") else (v * 1e3 if row["Metric Unit"].startswith("ms") else v)
+        t = tot[row["Kernel Name"]]
+        t[0] += 1
+        t[1] += v
+    total = sum(t[1] for t in tot.values()) or 1.0
+    with open(dst, "w") as f:
+        f.write(f"# ncu launch list of {title or src}\n\n`ncu --metrics gpu__time_duration.sum --clock-control none --csv`: kernel nodes of the CUDA "
+                "graphs are profiled one by one, cold-cache and serialised -- compare SHARES, not absolutes.\n\n"
+                "| kernel | launches | total us | avg us | share |\n|---|---|---|---|---|\n")
+        for k, (n, us) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{k[:70]}` | {n} | {us:.1f} | {us / n:.2f} | {100 * us / total:.1f}% |\n")
+
+
 def full(src, dst):
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
@@ -56,4 +77,4 @@ def full(src, dst):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "shares": shares}[sys.argv[1]](*sys.argv[2:])

@@ -195,7 +195,10 @@ def kernel_detail(torch, _native, dev, peak):
             y = torch.empty_like(x)
             dw = torch.empty_like(w)
             ws = _native.new_workspace(_native.backward_weight_workspace_bytes(B, 4, CT // 4, H, W, KSIZE, KSIZE), dev)
+            A1 = torch.linalg.qr(torch.randn(CT, CT, device=dev))[0].contiguous()
+            b1 = torch.randn(CT, device=dev)
             fns = {
+                "affine1x1 (8f.1: ActNorm+Conv1x1 glue, HBM-bound)": lambda: _native.affine1x1(x, A1, b1, out=y),
                 "forward_logdet": lambda: _native.forward(x, w, out=y, want_logdet=False),
                 "backward_input": lambda: _native.backward_input(dz, w, out=y),
                 "backward_weight": lambda: _native.backward_weight(dz, x, (KSIZE, KSIZE), out=dw, workspace=ws),
@@ -206,6 +209,11 @@ def kernel_detail(torch, _native, dev, peak):
             t_roof_us = max(nbytes / peak / 1e3, flops / ffma / 1e6)
             bound = "hbm" if nbytes / peak / 1e3 >= flops / ffma / 1e6 else "fp32"
             for name, fn in fns.items():
+                if name.startswith("affine1x1"):
+                    k_flops, k_roof, k_bound = 2.0 * B * H * W * CT * CT, None, "hbm"
+                    k_roof = max(nbytes / peak / 1e3, k_flops / ffma / 1e6)
+                else:
+                    k_flops, k_roof, k_bound = flops, t_roof_us, bound
                 for _ in range(3):
                     fn()
                 ts = []
@@ -220,8 +228,8 @@ def kernel_detail(torch, _native, dev, peak):
                 us = 1e3 * statistics.median(ts)
                 out.append({"kernel": name, "shape": [B, CT, H, W], "us": round(us, 2),
                             "GBps": round(nbytes / us / 1e3, 1), "frac_of_hbm_peak": round(nbytes / us / 1e3 / peak, 3),
-                            "TFLOPs": round(flops / us / 1e6, 2), "bound": bound,
-                            "frac_of_roofline": round(t_roof_us / us, 3), "images_per_s": round(B / us * 1e6)})
+                            "TFLOPs": round(k_flops / us / 1e6, 2), "bound": k_bound,
+                            "frac_of_roofline": round(k_roof / us, 3), "images_per_s": round(B / us * 1e6)})
             del x, dz, y
     return out
 

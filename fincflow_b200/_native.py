@@ -36,7 +36,7 @@ SYMBOLS = (
     "finc_forward_f32", "finc_backward_input_f32", "finc_backward_weight_workspace_bytes",
     "finc_backward_weight_f32", "finc_inverse_f32", "finc_apply_grad_mask_f32", "finc_logdet_f32",
     "finc_gaussian_logp_f32", "finc_debug_timestamps", "finc_prepared_weights_bytes", "finc_prepare_weights_f32",
-    "finc_squeeze_f32", "finc_unsqueeze_f32", "finc_adam_step_f32", "finc_allreduce_adam_f32",
+    "finc_squeeze_f32", "finc_unsqueeze_f32", "finc_adam_step_f32", "finc_allreduce_adam_f32", "finc_affine1x1_f32",
 )
 
 _lib = None
@@ -82,6 +82,8 @@ def load():
     lib.finc_squeeze_f32.argtypes = [p, p, i, i, i, i, p]
     lib.finc_unsqueeze_f32.restype = i
     lib.finc_unsqueeze_f32.argtypes = [p, p, i, i, i, i, p]
+    lib.finc_affine1x1_f32.restype = i
+    lib.finc_affine1x1_f32.argtypes = [p, p, p, p, i, i, ctypes.c_long, p]
     lib.finc_prepared_weights_bytes.restype = sz
     lib.finc_prepared_weights_bytes.argtypes = [i] + dims
     lib.finc_prepare_weights_f32.restype = i
@@ -320,6 +322,28 @@ def unsqueeze(x, out=None):
     B, C4, H, W = x.shape
     y = torch.empty((B, C4 // 4, 2 * H, 2 * W), dtype=torch.float32, device=x.device) if out is None else out
     _check(load().finc_unsqueeze_f32(x.data_ptr(), y.data_ptr(), B, C4, H, W, _stream(x)), "finc_unsqueeze_f32")
+    return y
+
+
+def affine1x1(x, A, bias=None, out=None):
+    """y[n,:,h,w] = A @ x[n,:,h,w] + bias: ActNorm followed by Conv1x1 (or their reverse / backward-data)
+    as one per-pixel affine map (layers/actnorm.py:14-52, layers/conv1x1.py:18-43)"""
+    x = _prep(x, "x")
+    A = _prep(A, "A")
+    _bind_device(x)
+    B, C = x.shape[0], x.shape[1]
+    HW = 1
+    for d in x.shape[2:]:
+        HW *= d
+    if tuple(A.shape) != (C, C):
+        raise FincNativeError(f"A must be [{C}, {C}], got {tuple(A.shape)}")
+    if bias is not None:
+        bias = _prep(bias, "bias")
+        if bias.numel() != C:
+            raise FincNativeError(f"bias must have {C} elements")
+    y = torch.empty_like(x) if out is None else out
+    _check(load().finc_affine1x1_f32(x.data_ptr(), A.data_ptr(), 0 if bias is None else bias.data_ptr(), y.data_ptr(),
+                                     B, C, HW, _stream(x)), "finc_affine1x1_f32")
     return y
 
 

@@ -236,6 +236,13 @@ int finc_unsqueeze_f32(const float* x, float* y, int B, int C4, int H, int W, vo
     return launch_squeeze(x, y, B, C4 / 4, 2 * H, 2 * W, true, (cudaStream_t)stream);
 }
 
+int finc_affine1x1_f32(const float* x, const float* A, const float* bias, float* y, int B, int C, long HW, void* stream) {
+    if (B < 0 || C < 1 || C > 4096 || HW < 1) return FINC_E_BADARG;
+    if (B == 0) return FINC_OK;
+    if (!x || !A || !y || x == y) return FINC_E_BADARG;
+    return launch_affine1x1(x, A, bias, y, B, C, HW, (cudaStream_t)stream);
+}
+
 size_t finc_prepared_weights_bytes(int kind, int B, int G, int C, int H, int W, int kH, int kW) {
     if (!shape_ok(B, G, C, H, W, kH, kW) || B < 1) return 0;
     const Shape s = mk(B, G, C, H, W, kH, kW, 0);

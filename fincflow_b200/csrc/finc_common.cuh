@@ -199,6 +199,7 @@ int launch_wgrad_naive(const float* dz, const float* x, float* dw, const Shape& 
 int launch_mask(float* dw, const Shape& s, cudaStream_t st);
 int launch_logdet(const float* w, float* logdet, bool accumulate, const Shape& s, cudaStream_t st);
 int launch_squeeze(const float* x, float* y, int B, int C, int H, int W, bool inverse, cudaStream_t st);
+int launch_affine1x1(const float* x, const float* A, const float* bias, float* y, int B, int C, long HW, cudaStream_t st);
 int launch_adam(float* p, const float* g, float* m, float* v, float* step, float lr, float b1, float b2, float eps,
                 long n, cudaStream_t st);
 int launch_allreduce_adam(const void* peer_grad, const void* peer_signal, void* local, float* param, float* m, float* v,

@@ -290,11 +290,84 @@ class GlowStep(_Chain):
         d["coupling"] = Coupling(size, width)
         self.glow_step = nn.Sequential(d)
 
+    fused = True  # ActNorm + Conv1x1 as one finc_affine1x1_f32 launch on CUDA tensors
+
     def forward(self, x):
+        if self.fused and x.is_cuda:
+            return _fused_glow_forward(self, x)
         return self._fwd(self.glow_step, x)
 
     def reverse(self, x):
+        if self.fused and x.is_cuda:
+            return _fused_glow_reverse(self, x)
         return self._rev(self.glow_step, x)
+
+
+class _Affine1x1Fn(torch.autograd.Function):
+    """y = A x + b per pixel on finc_affine1x1_f32; backward-data = the same kernel with A^T.
+    The C x C weight gradient is a tiny GEMM over all pixels (library bmm, glue level)."""
+
+    @staticmethod
+    def forward(ctx, x, A, b):
+        x = x.contiguous()
+        A = A.contiguous()
+        ctx.save_for_backward(x, A)
+        ctx.has_bias = b is not None
+        return _native.affine1x1(x, A, None if b is None else b.contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, A = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = _native.affine1x1(dy, A.t().contiguous()) if ctx.needs_input_grad[0] else None
+        dA = db = None
+        if ctx.needs_input_grad[1]:
+            dA = torch.bmm(dy.flatten(2), x.flatten(2).transpose(1, 2)).sum(0)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(dim=(0, 2, 3))
+        return dx, dA, db
+
+
+def affine_of(actnorm, conv1x1):
+    """(A, b) of ActNorm followed by Conv1x1: W ((x - t) * exp(-log_s)) = A x + b"""
+    W = conv1x1.W
+    if actnorm is None:
+        return W, None
+    A = W * torch.exp(-actnorm.log_scale).unsqueeze(0)
+    return A, -(A @ actnorm.translation)
+
+
+def _fused_glow_forward(self, x):
+    """GlowStep.forward with [ActNorm +] Conv1x1 as ONE per-pixel affine kernel (SURVEY.md 8f row 1);
+    same values and log-determinants as the layer-by-layer path (actnorm.py:14-64, conv1x1.py:18-43)."""
+    gs = self.glow_step
+    act = getattr(gs, "actnorm", None)
+    conv = gs.conv1x1
+    B, _, H, W = x.shape
+    logdet = 0
+    if act is not None and not act.initialized:
+        x, ld = act(x)                      # data-dependent init needs the un-fused statistics once
+        logdet = logdet + ld
+        act = None
+    elif act is not None:
+        logdet = logdet + act.logdet(x)
+    A, b = affine_of(act, conv)
+    y = _Affine1x1Fn.apply(x, A, b)
+    logdet = logdet + H * W * torch.slogdet(conv.W)[1]
+    y, ld = gs.coupling(y)
+    return y, logdet + ld
+
+
+def _fused_glow_reverse(self, z):
+    gs = self.glow_step
+    act = getattr(gs, "actnorm", None)
+    x = gs.coupling.reverse(z)
+    Winv = torch.inverse(gs.conv1x1.W)
+    if act is None:
+        return _native.affine1x1(x.contiguous(), Winv.contiguous())
+    assert act.initialized
+    Ainv = torch.exp(act.log_scale).unsqueeze(1) * Winv      # diag(exp(log_s)) W^-1
+    return _native.affine1x1(x.contiguous(), Ainv.contiguous(), act.translation.detach().contiguous())
 
 
 class FastFlowStep(_Chain):

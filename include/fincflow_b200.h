@@ -164,6 +164,16 @@ int finc_allreduce_adam_f32(const void* peer_grad, const void* peer_signal, void
 int finc_squeeze_f32(const float* x, float* y, int B, int C, int H, int W, void* stream);
 int finc_unsqueeze_f32(const float* x, float* y, int B, int C4, int H, int W, void* stream);
 
+/* Per-pixel affine map over the channel axis, x and y [B, C, HW] contiguous (NCHW with HW = H*W):
+ *   y[n, o, p] = sum_i A[o, i] * x[n, i, p] + (bias ? bias[o] : 0)           A: [C, C] row-major
+ * One pass for the glue that follows every FastFlowUnit in the reference's flow step
+ * (fastflow_cifar_multi_gpu.py:188-236): ActNorm (layers/actnorm.py:14-52) then Conv1x1
+ * (layers/conv1x1.py:18-43) compose to A = W diag(exp(-log_scale)), bias = -A translation; their
+ * reverse is A^-1 with bias = translation (instead of torch.inverse + conv2d per call), and the
+ * backward-data pass is A^T without bias.  x != y. */
+int finc_affine1x1_f32(const float* x, const float* A, const float* bias, float* y,
+                       int B, int C, long HW, void* stream);
+
 /* Prepared weight tables (optional fast path for fixed shapes, e.g. CUDA-graph replays).
  * The tiled kernels need the weights transposed / sweep-ordered in shared memory; by default
  * every launch re-stages them from the raw [G*C, C, kH, kW] tensor (~1-2 us).  A table prepared

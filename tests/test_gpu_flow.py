@@ -89,3 +89,76 @@ def test_builders_and_sampling_shapes():
         assert tuple(zs[-1].shape[1:]) == (96, 4, 4)
         rec = m64.reverse(n_samples=2, zs=zs)
         assert (rec - xb).abs().max().item() <= 1 and (rec != xb).float().mean().item() < 1e-3
+
+
+@pytest.mark.parametrize("shape", [(5, 12, 16, 16), (7, 24, 8, 8), (9, 48, 4, 4), (3, 96, 4, 4), (6, 4, 14, 14), (5, 8, 7, 7),
+                                   (4, 16, 5, 6), (3, 32, 3, 3), (2, 10, 5, 5), (256, 12, 16, 16), (1, 24, 16, 16)],
+                         ids=lambda s: "B{}C{}_{}x{}".format(*s))
+def test_affine1x1_is_actnorm_then_conv1x1(shape):
+    """finc_affine1x1_f32 == the reference's ActNorm followed by Conv1x1 (layers/actnorm.py:14-52,
+    layers/conv1x1.py:18-43), its reverse and its backward-data pass; fp64 formulas as the oracle"""
+    from fincflow_b200 import _native
+
+    B, C, H, W = shape
+    gen = torch.Generator().manual_seed(C * 100 + H)
+    x = torch.randn(B, C, H, W, generator=gen, dtype=torch.float64)
+    Wm = torch.linalg.qr(torch.randn(C, C, generator=gen, dtype=torch.float64))[0] + 0.05 * torch.randn(C, C, generator=gen, dtype=torch.float64)
+    t = torch.randn(C, generator=gen, dtype=torch.float64)
+    ls = 0.3 * torch.randn(C, generator=gen, dtype=torch.float64)
+    want = torch.einsum("oi,nihw->nohw", Wm, (x - t.view(1, C, 1, 1)) * torch.exp(-ls).view(1, C, 1, 1))
+    A = Wm * torch.exp(-ls).unsqueeze(0)
+    b = -(A @ t)
+    xd = x.float().cuda()
+    y = _native.affine1x1(xd, A.float().cuda(), b.float().cuda())
+    assert rel_err(y.cpu().numpy(), want.numpy()) <= 1e-5
+    # no bias == plain Conv1x1; A^T == its backward-data pass
+    y0 = _native.affine1x1(xd, Wm.float().cuda())
+    assert rel_err(y0.cpu().numpy(), torch.einsum("oi,nihw->nohw", Wm, x).numpy()) <= 1e-5
+    yt = _native.affine1x1(xd, Wm.t().contiguous().float().cuda())
+    assert rel_err(yt.cpu().numpy(), torch.einsum("io,nihw->nohw", Wm, x).numpy()) <= 1e-5
+    # reverse: A^-1 with bias = translation
+    Ainv = torch.exp(ls).unsqueeze(1) * torch.linalg.inv(Wm)
+    back = _native.affine1x1(y, Ainv.float().cuda(), t.float().cuda())
+    assert (back.cpu().double() - x).abs().max().item() <= 1e-4
+    # unaligned view (odd float offset): the kernel falls back to narrower vectors
+    buf = torch.zeros(xd.numel() + 1, device="cuda")
+    xv = buf[1:].view_as(xd)
+    xv.copy_(xd)
+    assert torch.equal(_native.affine1x1(xv, A.float().cuda(), b.float().cuda()), y) or \
+        rel_err(_native.affine1x1(xv, A.float().cuda(), b.float().cuda()).cpu().numpy(), want.numpy()) <= 1e-5
+
+
+@pytest.mark.parametrize("actnorm", [False, True])
+def test_fused_glow_step_equals_layerwise(actnorm):
+    """GlowStep with ActNorm+Conv1x1 on the fused kernel == the layer-by-layer PyTorch path:
+    values, log-determinant, every parameter gradient, reverse"""
+    from fincflow_b200.flows import GlowStep
+
+    torch.manual_seed(3)
+    size = (12, 8, 8)
+    step = GlowStep(size, actnorm=actnorm, width=16).cuda()
+    for p in step.glow_step.coupling.parameters():   # zero-initialised last conv would hide the path
+        p.data.normal_(0, 0.05)
+    x = torch.randn(6, *size, device="cuda") * 1.7 + 0.3
+    if actnorm:
+        step.fused = False
+        step(x)                                       # data-dependent init
+        step.glow_step.actnorm.log_scale.data.add_(0.1 * torch.randn(12, device="cuda"))
+    res = {}
+    for fused in (False, True):
+        step.fused = fused
+        step.zero_grad()
+        xi = x.clone().requires_grad_(True)
+        y, ld = step(xi)
+        (y.pow(2).sum() + (ld.sum() if torch.is_tensor(ld) else ld)).backward()
+        res[fused] = (y.detach(), torch.as_tensor(ld).detach().expand(6).clone(), xi.grad.clone(),
+                      {n: p.grad.clone() for n, p in step.named_parameters() if p.grad is not None})
+        with torch.no_grad():
+            assert (step.reverse(y.detach()) - x).abs().max().item() <= 1e-4
+    (y0, l0, g0, p0), (y1, l1, g1, p1) = res[False], res[True]
+    assert rel_err(y1.cpu().numpy(), y0.cpu().numpy()) <= 1e-5
+    assert rel_err(l1.cpu().numpy(), l0.cpu().numpy()) <= 1e-5
+    assert rel_err(g1.cpu().numpy(), g0.cpu().numpy()) <= 1e-5
+    assert p0.keys() == p1.keys()
+    for n in p0:
+        assert rel_err(p1[n].cpu().numpy(), p0[n].cpu().numpy()) <= 2e-5, n

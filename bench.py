@@ -234,6 +234,50 @@ def kernel_detail(torch, _native, dev, peak):
     return out
 
 
+def whole_flow_detail(torch, dev):
+    """context, not the metric: the COMPLETE CIFAR-10-shaped FInCFlow (3 blocks x 16 steps, Glow glue
+    with 512-wide coupling networks in PyTorch/cuDNN around the FInC kernels, fused ActNorm+Conv1x1
+    kernel) -- train step (forward, backward, FInC mask, Adam) and model.sample at batch 256."""
+    from fincflow_b200 import flows
+
+    torch.manual_seed(0)
+    B = PER_GPU_BATCH
+    m = flows.fastflow_cifar10().to(dev)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    x = torch.randint(0, 256, (B, 3, 32, 32), device=dev).float()
+
+    def train():
+        opt.zero_grad(set_to_none=True)
+        _, logp = m(x)
+        (-(logp.sum() / B)).backward()
+        m.apply(flows.clear_grad)
+        opt.step()
+
+    def sample():
+        with torch.no_grad():
+            m.sample(B)
+
+    out = {"model": "fincflow_b200.flows.fastflow_cifar10() (3 blocks x 16 FastFlowSteps, coupling width 512), batch 256, "
+                    "random init; glue in PyTorch (cuDNN TF32 default), FInC units / squeeze / ActNorm+Conv1x1 on our kernels",
+           "n_params": sum(p.numel() for p in m.parameters())}
+    for name, fn in (("train_step", train), ("sample", sample)):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        out[name + "_ms"] = round(ms, 2)
+        out[name + "_images_per_s"] = round(B / ms * 1e3, 1)
+    del m, opt
+    torch.cuda.empty_cache()
+    return out
+
+
 def main_ours(args):
     import torch
 
@@ -361,6 +405,12 @@ def main_ours(args):
     line = None
     if rank == 0:
         detail = kernel_detail(torch, _native, dev, peak) if (world == 1 and not args.no_detail) else None
+        whole = None
+        if world == 1 and not args.no_detail:
+            try:
+                whole = whole_flow_detail(torch, dev)
+            except Exception as e:  # context only: never fail the bench line over it
+                whole = {"error": repr(e)}
         cpu = None
         if world == 1 and not args.no_cpu:
             r = run_reference_cpu(steps=6, warmup=1, max_seconds=25.0)
@@ -387,7 +437,7 @@ def main_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clocks,
-            "kernels": detail,
+            "kernels": detail, "whole_flow_context": whole,
         }
         emit(line)
     if world > 1:

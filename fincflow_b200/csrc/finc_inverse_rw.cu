@@ -16,7 +16,6 @@ FINC_RW_EXTERN(3)
 FINC_RW_EXTERN(4)
 FINC_RW_EXTERN(6)
 FINC_RW_EXTERN(12)
-FINC_RW_EXTERN(24)
 #undef FINC_RW_EXTERN
 }  // namespace rw
 
@@ -32,16 +31,16 @@ int env_int(const char* name, int dflt) {
 bool rw_shape_supported(const Shape& s) {
     if (!((s.kH == 3 && s.kW == 3) || (s.kH == 5 && s.kW == 5))) return false;
     const int C = s.C;
-    if (!(C == 1 || C == 2 || C == 3 || C == 4 || C == 6 || C == 12 || C == 24)) return false;
+    // (C = 24 stays on the shared-memory wavefront kernel: its 276-term corner solve, run redundantly
+    //  by the 8 lanes of a pixel, makes the register-window variant slower -- tools/ab_inverse.py)
+    if (!(C == 1 || C == 2 || C == 3 || C == 4 || C == 6 || C == 12)) return false;
     if (s.W > 32 || (long)C * s.H * s.W * 4 > 32 * 1024) return false;
     int WP = 4;
     while (WP < s.W) WP *= 2;
-    // some instantiated P must fit the warp (C = 24 needs P >= 4: W <= 8)
-    if (C == 24 && WP > 8) return false;
+    // some instantiated P must fit the warp
     if (s.kH == 5 && C == 4 && WP > 16) return false;   // 5x5, C = 4: P = 2 only
     if (s.kH == 5 && C == 12 && WP > 8) return false;   // 5x5, C = 12: P = 4 only
     if (s.kH == 5 && C == 6 && WP > 16) return false;   // 5x5, C = 6: P >= 2
-    if (s.kH == 5 && C == 24 && WP > 4) return false;   // 5x5, C = 24: P = 8 only
     return true;
 }
 
@@ -53,7 +52,6 @@ int launch_inverse_rw(const float* z, const float* w, float* x, const Shape& s, 
     if (!enabled) return 0;
     if (!((s.kH == 3 && s.kW == 3) || (s.kH == 5 && s.kW == 5))) return 0;
     const int C = s.C, KS = s.kH;
-    if (!(C == 1 || C == 2 || C == 3 || C == 4 || C == 6 || C == 12 || C == 24)) return 0;
     if (!rw_shape_supported(s)) return 0;
     const long tile_floats_l = (long)C * s.H * s.W;
     RwArgs a{};
@@ -92,8 +90,7 @@ int launch_inverse_rw(const float* z, const float* w, float* x, const Shape& s, 
             case 3: ok = rw::rw_supported(3, KS, KS, P); break;
             case 4: ok = rw::rw_supported(4, KS, KS, P); break;
             case 6: ok = rw::rw_supported(6, KS, KS, P); break;
-            case 12: ok = rw::rw_supported(12, KS, KS, P); break;
-            default: ok = rw::rw_supported(24, KS, KS, P); break;
+            default: ok = rw::rw_supported(12, KS, KS, P); break;
         }
         if (ok) cand[nc++] = P;
     }
@@ -105,7 +102,12 @@ int launch_inverse_rw(const float* z, const float* w, float* x, const Shape& s, 
     }
     if (C == 6 && KS == 3 && nc > 1 && P == 1) P = 2;  // P = 2 keeps the C = 6 weights in registers
     P = env_int("FINC_RW_P", P);
-    const int NSTK = 32 / (WP * P);
+    // stacks per warp: all 32/(WP*P) lanes groups when the batch can fill the SMs, fewer (idle lanes,
+    // more warps) when it cannot
+    int NSTK = 32 / (WP * P);
+    while (NSTK > 1 && tiles / NSTK < ctas_max * 4) NSTK /= 2;
+    NSTK = env_int("FINC_RW_NSTK", NSTK);
+    a.NSTK = NSTK;
     const int maxw_k = rw::rw_max_warps(C, KS, KS, P);
     const int maxw = env_int("FINC_RW_WARPS", maxw_k) < maxw_k ? env_int("FINC_RW_WARPS", maxw_k) : maxw_k;
 
@@ -150,8 +152,7 @@ int launch_inverse_rw(const float* z, const float* w, float* x, const Shape& s, 
             case 3: rc = rw::dispatch_ck<3, 3>(P, a, grid, nwarps, smem, st); break;
             case 4: rc = rw::dispatch_ck<4, 3>(P, a, grid, nwarps, smem, st); break;
             case 6: rc = rw::dispatch_ck<6, 3>(P, a, grid, nwarps, smem, st); break;
-            case 12: rc = rw::dispatch_ck<12, 3>(P, a, grid, nwarps, smem, st); break;
-            default: rc = rw::dispatch_ck<24, 3>(P, a, grid, nwarps, smem, st); break;
+            default: rc = rw::dispatch_ck<12, 3>(P, a, grid, nwarps, smem, st); break;
         }
     } else {
         switch (C) {
@@ -160,8 +161,7 @@ int launch_inverse_rw(const float* z, const float* w, float* x, const Shape& s, 
             case 3: rc = rw::dispatch_ck<3, 5>(P, a, grid, nwarps, smem, st); break;
             case 4: rc = rw::dispatch_ck<4, 5>(P, a, grid, nwarps, smem, st); break;
             case 6: rc = rw::dispatch_ck<6, 5>(P, a, grid, nwarps, smem, st); break;
-            case 12: rc = rw::dispatch_ck<12, 5>(P, a, grid, nwarps, smem, st); break;
-            default: rc = rw::dispatch_ck<24, 5>(P, a, grid, nwarps, smem, st); break;
+            default: rc = rw::dispatch_ck<12, 5>(P, a, grid, nwarps, smem, st); break;
         }
     }
     if (rc == FINC_E_UNSUPPORTED) return prepared ? FINC_E_UNSUPPORTED : 0;

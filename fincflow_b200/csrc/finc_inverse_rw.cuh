@@ -41,6 +41,7 @@ struct RwArgs {
     int T;         // tiles per stack
     int S;         // pipeline stages per warp (1 or 2)
     int WP;        // column slots per stack (power of two >= W)
+    int NSTK;      // stacks per warp in use (<= 32 / (WP * P); lanes beyond them idle)
     int gsplit;
     int bulk;
     int tile_floats;
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(Cfg<C, KH, KW, P>::MAXW * 32, 1) inverse_rw_ke
     const Shape& s = a.s;
     const int H = s.H, W = s.W;
     const int HW = H * W;
-    const int NSTK = 32 / (a.WP * P);
+    const int NSTK = a.NSTK;
     const int item_tiles = NSTK * a.T;
     const int stage_floats = NSTK * a.stack_stride;
     const int wk_pad = (a.wk_floats + 31) & ~31;
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(Cfg<C, KH, KW, P>::MAXW * 32, 1) inverse_rw_ke
     const int p = lane % P;
     const int j = (lane / P) % a.WP;   // sweep column
     const int q = lane / (P * a.WP);   // stack inside the item
-    const bool col_on = j < W;
+    const bool col_on = j < W && q < NSTK;
 
     long k = 0;
     for (long item = gw; item < a.n_items; item += gstride, ++k) {
@@ -395,7 +396,7 @@ constexpr bool rw_supported(int C, int KH, int KW, int P) {
     if (C <= 3 && P > 1) return false;
     if (C == 4 && P > 2) return false;
     if (C >= 12 && P == 2) return false;   // 1 and 4 cover the small- and large-batch regimes
-    if (C == 24 && P < 4) return false;
+    if (C > 12) return false;
     return true;
 }
 constexpr int rw_max_warps(int C, int KH, int KW, int P) {

@@ -166,10 +166,11 @@ int launch_conv_fast(const float* x, const float* w, float* y, float* logdet, bo
     if ((long)sub_per_tile >= 65536) return 0;
     a.m_nstrip = magic(a.nstrip); a.m_h = magic(s.H); a.m_nob = magic(a.nob);
 
-    // chunk: about one sub-item per consumer thread (512), at most 24 KB, and small enough that
+    // chunk: about one sub-item per consumer thread (512), at most 48 KB, and small enough that
     // every SM gets a chunk when the batch is small
-    int CH = (kMaxConsumerWarps * 32 + sub_per_tile - 1) / sub_per_tile;
-    while (CH > 1 && (long)CH * a.tile_floats * 4 > 24 * 1024) --CH;
+    int CH = (kMaxConsumerWarps * 32) / sub_per_tile;  // (rounded down: one pass of the consumer threads per chunk)
+    if (CH < 1) CH = 1;
+    while (CH > 1 && (long)CH * a.tile_floats * 4 > 48 * 1024) --CH;
     if (CH > spread) CH = (int)spread;
     if (CH > s.B) CH = s.B;
     if (CH < 1) CH = 1;

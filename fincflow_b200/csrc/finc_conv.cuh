@@ -181,7 +181,9 @@ __device__ __forceinline__ void conv_sub(const float* __restrict__ xt, const flo
             }
         }
     };
-    if constexpr (CT > 0 && CT * KH * KW * OB * WT <= 1400) {
+    // full unrolling only while the straight-line code of both padding variants stays inside the
+    // instruction cache (C = 6, OB = 6 fully unrolled: 41 % of the stall samples were instruction fetch)
+    if constexpr (CT > 0 && CT * KH * KW * OB * WT <= 1000) {
 #pragma unroll
         for (int cin = 0; cin < CT; ++cin) body(cin);
     } else {

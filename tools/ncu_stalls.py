@@ -26,6 +26,19 @@ for r in csv.reader(io.StringIO(src)):
         secs.append(cur)
     elif cur is not None:
         cur["rows"].append(r)
+import re
+
+
+def sig(name):
+    """kernel identity that survives the different demanglings of the raw and source pages"""
+    m = re.search(r"(\w+_kernel)<([^>]*)>", name)
+    if not m:
+        return name.split("(")[0].split("::")[-1], ()
+    return m.group(1), tuple(re.findall(r"\d+", re.sub(r"\(int\)|\(bool\)", "", m.group(2))))
+
+
+# the source page has one section per profiled launch, in launch order, like the raw page; pair them by
+# position but verify the kernel identity (a mismatch means the pages are laid out differently)
 seen = set()
 for k, r in enumerate(data):
     name = r[idx["Kernel Name"]]
@@ -33,13 +46,15 @@ for k, r in enumerate(data):
     if key in seen:
         continue
     seen.add(key)
+    sec = secs[k] if k < len(secs) and sig(secs[k]["name"]) == sig(name) else next(
+        (s_ for s_ in secs if sig(s_["name"]) == sig(name)), None)
     print("=" * 100)
     print(name[:110])
     for w in WANT:
         if w in idx:
             print(f"  {w:70s} {r[idx[w]]}")
-    if k < len(secs):
-        s = secs[k]
+    if sec is not None:
+        s = sec
         h, d = s["rows"][0], s["rows"][1:]
         tot = sum(int(x[2]) for x in d) or 1
         print(f"  stall samples ({tot}):", end=" ")

@@ -45,12 +45,14 @@ struct WgArgs {
     Shape s;
     unsigned flags;
     int CH, S, bulk, tile_floats;
+    int tile_stride;           // floats between tiles in shared memory: tile_floats + 4, so that lanes that differ
+                               // in the tile index (fastest in the slot order) hit different 16-byte bank groups
     int nob, nstrip, RR, rpr;  // output blocks, strips per row, row ranges per tile, rows per range
     int slots, SP;             // slots per combo and its padded size (power of two <= 32, or multiple of 32)
     int ncombo, cpc;           // combos in total / per CTA
     int X, Z, nchunks;
     unsigned long long* dbg;
-    unsigned m_nstrip, m_rr;
+    unsigned m_nstrip, m_ch;
 };
 
 __device__ __forceinline__ unsigned fastdiv(unsigned n, unsigned m) { return m ? __umulhi(n, m) : n; }
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__((max_consumer_warps(OB, KH) + 1) * 32, 1) wgra
     float* front = reinterpret_cast<float*>(smem_raw);  // kFrontPad zero floats
     float* zrow = front + 8;
     float* bufs = front + kFrontPad;
-    const int half = a.CH * a.tile_floats;  // floats of x (or dz) tiles per stage
+    const int half = a.CH * a.tile_stride;  // floats of x (or dz) tiles per stage
     float* red = bufs + (size_t)a.S * 2 * half + 8;
     const int nthreads_c = blockDim.x - 32;
     const int nseg_max = nthreads_c / (a.SP < 32 ? a.SP : 32);
@@ -164,8 +166,8 @@ __global__ void __launch_bounds__((max_consumer_warps(OB, KH) + 1) * 32, 1) wgra
         float* ds = xs + half;
         for (int t = lane; t < nt; t += 32) {
             const long off = ((long)(n0 + t) * s.G + g) * a.tile_floats;
-            bulk_g2s(xs + t * a.tile_floats, a.x + off, (uint32_t)(a.tile_floats * 4), &full[st]);
-            bulk_g2s(ds + t * a.tile_floats, a.dz + off, (uint32_t)(a.tile_floats * 4), &full[st]);
+            bulk_g2s(xs + t * a.tile_stride, a.x + off, (uint32_t)(a.tile_floats * 4), &full[st]);
+            bulk_g2s(ds + t * a.tile_stride, a.dz + off, (uint32_t)(a.tile_floats * 4), &full[st]);
         }
     };
 
@@ -205,11 +207,12 @@ __global__ void __launch_bounds__((max_consumer_warps(OB, KH) + 1) * 32, 1) wgra
         const bool lane_on = cl < a.cpc && combo < a.ncombo && slot < a.slots;
         const int ci = lane_on ? combo / a.nob : 0;
         const int ob = lane_on ? combo - ci * a.nob : 0;
-        unsigned q1 = fastdiv((unsigned)slot, a.m_nstrip);
-        const int strip = slot - (int)q1 * a.nstrip;
-        const unsigned q2 = fastdiv(q1, a.m_rr);
-        const int rr = (int)q1 - (int)q2 * a.RR;
-        const int t = (int)q2;
+        // slot = (rr * nstrip + strip) * CH + t: the tile index varies fastest across lanes
+        const unsigned q1 = fastdiv((unsigned)slot, a.m_ch);
+        const int t = slot - (int)q1 * a.CH;
+        const unsigned q2 = fastdiv(q1, a.m_nstrip);
+        const int strip = (int)q1 - (int)q2 * a.nstrip;
+        const int rr = (int)q2;
         const int w0 = strip * WT;
         const int h0 = rr * a.rpr, h1 = min(H, h0 + a.rpr);
         const int nvalid_o = min(OB, C - ob * OB);
@@ -237,15 +240,15 @@ __global__ void __launch_bounds__((max_consumer_warps(OB, KH) + 1) * 32, 1) wgra
                 for (int tt = 0; tt < nt; ++tt) {
                     const long off = ((long)(n0 + tt) * s.G + g) * a.tile_floats;
                     for (int e = threadIdx.x; e < a.tile_floats; e += nthreads_c) {
-                        xs[tt * a.tile_floats + e] = a.x[off + e];
-                        ds[tt * a.tile_floats + e] = a.dz[off + e];
+                        xs[tt * a.tile_stride + e] = a.x[off + e];
+                        ds[tt * a.tile_stride + e] = a.dz[off + e];
                     }
                 }
                 asm volatile("bar.sync 1, %0;" ::"r"(nthreads_c) : "memory");
             }
-            if (lane_on && t < nt && h0 < h1) {
-                const float* xc = xs + t * a.tile_floats + ci * HW;
-                const float* dzc = ds + t * a.tile_floats + (ob * OB) * HW;
+            if (lane_on && rr < a.RR && t < nt && h0 < h1) {
+                const float* xc = xs + t * a.tile_stride + ci * HW;
+                const float* dzc = ds + t * a.tile_stride + (ob * OB) * HW;
                 if (right) sweep<OB, WT, KH, KW, true>(acc, xc, dzc, zrow, nvalid_o, H, W, HW, w0, r0, h0, h1);
                 else sweep<OB, WT, KH, KW, false>(acc, xc, dzc, zrow, nvalid_o, H, W, HW, w0, r0, h0, h1);
             }
@@ -438,7 +441,7 @@ bool make_plan(const Shape& s, Plan* p, int sm_div = 1) {
             int x = sms / (s.G * q.Z);
             if (x < 1) x = 1;
             int CH = (s.B + x - 1) / x;  // one chunk per CTA when it fits
-            const long ch_mem = (long)((budget - 16384) / (2 * tile_bytes));
+            const long ch_mem = (long)((budget - 16384) / (2 * (tile_bytes + 16)));
             if (CH > ch_mem) CH = (int)ch_mem;
             if (CH > 32) CH = 32;
             if (f_ch && CH > f_ch) CH = f_ch;
@@ -467,7 +470,7 @@ bool make_plan(const Shape& s, Plan* p, int sm_div = 1) {
             q.threads = ((q.cpc * q.SP + 31) / 32 + 1) * 32;
             const int nseg = (q.threads - 32) / (q.SP < 32 ? q.SP : 32);
             for (;;) {
-                q.smem = (size_t)kFrontPad * 4 + (size_t)q.S * 2 * CH * tile_bytes + 32 + (size_t)(nseg * nacc + 2) * 4 +
+                q.smem = (size_t)kFrontPad * 4 + (size_t)q.S * 2 * CH * (tile_bytes + 16) + 32 + (size_t)(nseg * nacc + 2) * 4 +
                          2 * q.S * 8 + 64;
                 if (q.smem <= budget || q.S == 1) break;
                 --q.S;
@@ -535,8 +538,9 @@ int launch_wgrad_fast(const float* dz, const float* x, float* dw, float* workspa
     a.partial = workspace + kCounterBytes / 4;
     a.CH = p.CH; a.S = p.S; a.nob = p.nob; a.nstrip = p.nstrip; a.RR = p.RR; a.rpr = p.rpr;
     a.slots = p.slots; a.SP = p.SP; a.ncombo = p.ncombo; a.cpc = p.cpc; a.X = p.X; a.Z = p.Z; a.nchunks = p.nchunks;
-    a.m_nstrip = magic(p.nstrip); a.m_rr = magic(p.RR);
+    a.m_nstrip = magic(p.nstrip); a.m_ch = magic(p.CH);
     a.tile_floats = s.C * s.H * s.W;
+    a.tile_stride = a.tile_floats + 4;
     a.bulk = (a.tile_floats % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
              ((reinterpret_cast<uintptr_t>(dz) & 15) == 0);
     if (a.X > 1 && !(flags & FINC_FLAG_WORKSPACE_CLEAN)) {

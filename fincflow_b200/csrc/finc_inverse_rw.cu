@@ -105,7 +105,7 @@ int launch_inverse_rw(const float* z, const float* w, float* x, const Shape& s, 
     // stacks per warp: all 32/(WP*P) lanes groups when the batch can fill the SMs, fewer (idle lanes,
     // more warps) when it cannot
     int NSTK = 32 / (WP * P);
-    while (NSTK > 1 && tiles / NSTK < ctas_max * 4) NSTK /= 2;
+    while (NSTK > 1 && tiles / NSTK < ctas_max * 2) NSTK /= 2;   // (x4 was measured slower at batch 256)
     NSTK = env_int("FINC_RW_NSTK", NSTK);
     a.NSTK = NSTK;
     const int maxw_k = rw::rw_max_warps(C, KS, KS, P);

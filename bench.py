@@ -291,9 +291,13 @@ def main_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     pg = None
+    host_cpus = None
     if world > 1:
         import torch.distributed as dist
 
+        from fincflow_b200.distributed import bind_host_cores
+
+        host_cpus = bind_host_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
     K, Wm = args.steps, max(args.warmup, 3)
@@ -354,8 +358,10 @@ def main_ours(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host0 = time.perf_counter()
     for i in range(K):
         e2e_runner.step(i % ESLOT)
+    host_ms_per_step = 1e3 * (time.perf_counter() - t_host0) / K   # CPU time to ENQUEUE a step (must stay below ms_per_step)
     e2e_runner.drain()  # the timed region ends when the last results have reached the host buffers
     e1.record()
     barrier()
@@ -431,6 +437,7 @@ def main_ours(args):
                 "inverse_sampling": round(B * world / (pm["inverse"] * 1e-3))},
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_ms / K, 4), "api": "fincflow_b200.stack.HotPathRunner(host_io=True).step",
+                    "host_enqueue_ms_per_step": round(host_ms_per_step, 4), "host_cpus": host_cpus,
                     "check_mean_logp_level0": logp_last},
             "gpu_launches": launches * K,
             "gpu_launches_per_step": launches,

@@ -91,3 +91,20 @@ def test_compat_shims_have_the_pybind_signature():
 
     for obj in (compat.cinc_cuda_level1, compat.cinc_cuda_level2):
         assert list(inspect.signature(obj.inverse).parameters) == ["input", "kernel", "output"]
+
+
+def test_plan_host_cores():
+    from fincflow_b200.distributed import _parse_cpulist, plan_host_cores
+
+    assert _parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    allowed = range(16)
+    # no topology: even split
+    assert plan_host_cores(3, 8, allowed) == [6, 7]
+    # two NUMA nodes, four GPUs each: every rank gets CPUs of ITS node, disjoint from its peers
+    nodes = [0, 0, 0, 0, 1, 1, 1, 1]
+    node_cpus = {0: list(range(0, 8)), 1: list(range(8, 16))}
+    got = [plan_host_cores(r, 8, allowed, nodes, node_cpus) for r in range(8)]
+    assert got[0] == [0, 1] and got[3] == [6, 7] and got[4] == [8, 9] and got[7] == [14, 15]
+    assert len({c for g in got for c in g}) == 16
+    # more ranks than CPUs on a node: fall back to the even split of the allowed set
+    assert plan_host_cores(1, 4, range(4), [0, 0, 0, 0], {0: [0, 1]}) == [1]

@@ -2,6 +2,8 @@
 // (kernel: finc_conv.cuh; instantiations: finc_conv_c<N>.cu).
 #include "finc_conv.cuh"
 
+#include <cstdlib>
+
 namespace finc {
 
 using conv::ConvArgs;
@@ -162,9 +164,21 @@ int launch_conv_fast(const float* x, const float* w, float* y, float* logdet, bo
     const int OB = wp.OB;
     a.nob = wp.nob;
     a.wk_floats = (int)(a.gsplit ? wp.wk_per_g : wp.wk_per_g * s.G);
-    const int sub_per_tile = a.nob * s.H * a.nstrip;
+    // two output rows per sub-item for the HBM-bound small-channel levels once the batch is large
+    // enough to keep every consumer thread busy anyway (amortises strip loads, weight loads and index
+    // arithmetic; FINC_CONV_RB=1/2 overrides)
+    a.RB = 1;
+    if (ct >= 1 && ct <= 3 && OB == ct && WT == 4 && s.kH == 3 && s.H >= 2 &&
+        spread * a.nob * s.H * a.nstrip >= 4L * kMaxConsumerWarps * 32)
+        a.RB = 2;
+    {
+        static const char* e = getenv("FINC_CONV_RB");
+        if (e && (e[0] == '1' || (e[0] == '2' && ct >= 1 && ct <= 3 && OB == ct && WT == 4 && s.kH == 3))) a.RB = e[0] - '0';
+    }
+    a.HR = (s.H + a.RB - 1) / a.RB;
+    const int sub_per_tile = a.nob * a.HR * a.nstrip;
     if ((long)sub_per_tile >= 65536) return 0;
-    a.m_nstrip = magic(a.nstrip); a.m_h = magic(s.H); a.m_nob = magic(a.nob);
+    a.m_nstrip = magic(a.nstrip); a.m_h = magic(a.HR); a.m_nob = magic(a.nob);
 
     // chunk: about one sub-item per consumer thread (512), at most 48 KB, and small enough that
     // every SM gets a chunk when the batch is small

@@ -52,6 +52,8 @@ struct ConvArgs {
     int tile_floats;  // C*H*W
     int wk_floats;    // weight floats in smem (all groups or one)
     int nstrip;       // W / WT
+    int RB;           // output rows per sub-item (1, or 2 for the row-blocked variant)
+    int HR;           // row blocks per tile = ceil(H / RB)
     unsigned m_nstrip, m_h, m_nob;  // magic multipliers for division by nstrip, H, nob
     unsigned long long* dbg;  // debug timestamps (nullptr = off)
     int nblk;         // image blocks = ceil(B / CH)
@@ -94,33 +96,39 @@ __device__ __forceinline__ void ld_halo(const float* p, float* out) {
     }
 }
 
-// one sub-item: OB output channels x WT pixels of row h.  RIGHT = padded on the right.
-template <int CT, int OB, int WT, int KH, int KW, bool RIGHT>
+// one sub-item: OB output channels x WT pixels of rows h .. h+RB-1.  RIGHT = padded on the right.
+// RB = 2 (row-blocked variant for the HBM-bound small-channel levels at large batch): the KH+1 input
+// row strips and every weight vector are loaded once for two output rows, and the index arithmetic
+// of a sub-item is amortised over twice the FMAs.
+template <int CT, int OB, int WT, int KH, int KW, bool RIGHT, int RB>
 __device__ __forceinline__ void conv_sub(const float* __restrict__ xt, const float* __restrict__ zrow,
                                          const float* __restrict__ wg, float* __restrict__ yt, int C, int H, int W,
                                          int HW, int h, int w0, int r0, int ob, int nob) {
     constexpr int OBP = ObPad<OB>::value;
     constexpr int HALO = KW - 1;
+    constexpr int NR = KH + RB - 1;   // input rows feeding the RB output rows
     const int nobp = (CT > 0 ? (CT + OB - 1) / OB : nob) * OBP;
-    const float* midp[KH];
-    const float* halop[KH];
-    int mstr[KH], hstr[KH];
+    const float* midp[NR];
+    const float* halop[NR];
+    int mstr[NR], hstr[NR];
 #pragma unroll
-    for (int ap = 0; ap < KH; ++ap) {
-        const int hh = h + r0 + ap;
+    for (int ar = 0; ar < NR; ++ar) {
+        const int hh = h + r0 + ar;
         const bool ok = hh >= 0 && hh < H;
         const float* row = xt + hh * W + w0;
         const bool hok = ok && (RIGHT ? (w0 + WT < W) : (w0 > 0));
-        midp[ap] = ok ? row : zrow;
-        mstr[ap] = ok ? HW : 0;
-        halop[ap] = hok ? (RIGHT ? row + WT : row - HALO) : zrow;
-        hstr[ap] = hok ? HW : 0;
+        midp[ar] = ok ? row : zrow;
+        mstr[ar] = ok ? HW : 0;
+        halop[ar] = hok ? (RIGHT ? row + WT : row - HALO) : zrow;
+        hstr[ar] = hok ? HW : 0;
     }
-    float acc[OB][WT];
+    float acc[RB][OB][WT];
 #pragma unroll
-    for (int o = 0; o < OB; ++o)
+    for (int rb = 0; rb < RB; ++rb)
 #pragma unroll
-        for (int q = 0; q < WT; ++q) acc[o][q] = 0.f;
+        for (int o = 0; o < OB; ++o)
+#pragma unroll
+            for (int q = 0; q < WT; ++q) acc[rb][o][q] = 0.f;
     const float* wb = wg + ob * OBP;
 
     // the vector halo (redirected as a whole to the zero strip) needs the halo to fit in the
@@ -134,56 +142,83 @@ __device__ __forceinline__ void conv_sub(const float* __restrict__ xt, const flo
             colok[q] = col >= 0 && col < W;
         }
     }
-    auto body = [&](int cin) {
-#pragma unroll
-        for (int ap = 0; ap < KH; ++ap) {
-            float xs[WT + HALO];
-            if constexpr (VHALO) {
-                if constexpr (RIGHT) {
-                    ldn<WT>(midp[ap] + cin * mstr[ap], xs);
-                    ld_halo<WT, HALO>(halop[ap] + cin * hstr[ap], xs + WT);
-                } else {
-                    ld_halo<WT, HALO>(halop[ap] + cin * hstr[ap], xs);
-                    ldn<WT>(midp[ap] + cin * mstr[ap], xs + HALO);
-                }
+    auto load_strip = [&](int cin, int ar, float (&xs)[WT + HALO]) {
+        if constexpr (VHALO) {
+            if constexpr (RIGHT) {
+                ldn<WT>(midp[ar] + cin * mstr[ar], xs);
+                ld_halo<WT, HALO>(halop[ar] + cin * hstr[ar], xs + WT);
             } else {
-                const float* mp = midp[ap] + cin * mstr[ap];  // zero strip when the row is outside
-                ldn<WT>(mp, xs + (RIGHT ? 0 : HALO));
+                ld_halo<WT, HALO>(halop[ar] + cin * hstr[ar], xs);
+                ldn<WT>(midp[ar] + cin * mstr[ar], xs + HALO);
+            }
+        } else {
+            const float* mp = midp[ar] + cin * mstr[ar];  // zero strip when the row is outside
+            ldn<WT>(mp, xs + (RIGHT ? 0 : HALO));
 #pragma unroll
-                for (int q = 0; q < HALO; ++q) {
-                    const float v = mp[RIGHT ? WT + q : q - HALO];
-                    xs[RIGHT ? WT + q : q] = colok[q] ? v : 0.f;
+            for (int q = 0; q < HALO; ++q) {
+                const float v = mp[RIGHT ? WT + q : q - HALO];
+                xs[RIGHT ? WT + q : q] = colok[q] ? v : 0.f;
+            }
+        }
+    };
+    auto load_w = [&](const float* wp, int bp, float (&wv)[OB]) {
+        if constexpr (OBP % 4 == 0) {
+#pragma unroll
+            for (int v = 0; v < OBP / 4; ++v) {
+                const float4 f = *reinterpret_cast<const float4*>(wp + bp * nobp + 4 * v);
+                if (4 * v + 0 < OB) wv[4 * v + 0] = f.x;
+                if (4 * v + 1 < OB) wv[4 * v + 1] = f.y;
+                if (4 * v + 2 < OB) wv[4 * v + 2] = f.z;
+                if (4 * v + 3 < OB) wv[4 * v + 3] = f.w;
+            }
+        } else if constexpr (OBP == 2) {
+            const float2 f = *reinterpret_cast<const float2*>(wp + bp * nobp);
+            wv[0] = f.x; wv[1] = f.y;
+        } else {
+            wv[0] = wp[bp * nobp];
+        }
+    };
+    auto body = [&](int cin) {
+        if constexpr (RB == 1) {
+#pragma unroll
+            for (int ap = 0; ap < KH; ++ap) {
+                float xs[WT + HALO];
+                load_strip(cin, ap, xs);
+                const float* wp = wb + (size_t)((cin * KH + ap) * KW) * nobp;
+#pragma unroll
+                for (int bp = 0; bp < KW; ++bp) {
+                    float wv[OB];
+                    load_w(wp, bp, wv);
+#pragma unroll
+                    for (int o = 0; o < OB; ++o)
+#pragma unroll
+                        for (int q = 0; q < WT; ++q) acc[0][o][q] = fmaf(wv[o], xs[q + bp], acc[0][o][q]);
                 }
             }
-            const float* wp = wb + (size_t)((cin * KH + ap) * KW) * nobp;
+        } else {
+            float xs[NR][WT + HALO];
 #pragma unroll
-            for (int bp = 0; bp < KW; ++bp) {
-                float wv[OB];
-                if constexpr (OBP % 4 == 0) {
+            for (int ar = 0; ar < NR; ++ar) load_strip(cin, ar, xs[ar]);
 #pragma unroll
-                    for (int v = 0; v < OBP / 4; ++v) {
-                        const float4 f = *reinterpret_cast<const float4*>(wp + bp * nobp + 4 * v);
-                        if (4 * v + 0 < OB) wv[4 * v + 0] = f.x;
-                        if (4 * v + 1 < OB) wv[4 * v + 1] = f.y;
-                        if (4 * v + 2 < OB) wv[4 * v + 2] = f.z;
-                        if (4 * v + 3 < OB) wv[4 * v + 3] = f.w;
-                    }
-                } else if constexpr (OBP == 2) {
-                    const float2 f = *reinterpret_cast<const float2*>(wp + bp * nobp);
-                    wv[0] = f.x; wv[1] = f.y;
-                } else {
-                    wv[0] = wp[bp * nobp];
+            for (int ap = 0; ap < KH; ++ap) {
+                const float* wp = wb + (size_t)((cin * KH + ap) * KW) * nobp;
+#pragma unroll
+                for (int bp = 0; bp < KW; ++bp) {
+                    float wv[OB];
+                    load_w(wp, bp, wv);
+#pragma unroll
+                    for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+                        for (int o = 0; o < OB; ++o)
+#pragma unroll
+                            for (int q = 0; q < WT; ++q) acc[rb][o][q] = fmaf(wv[o], xs[ap + rb][q + bp], acc[rb][o][q]);
                 }
-#pragma unroll
-                for (int o = 0; o < OB; ++o)
-#pragma unroll
-                    for (int q = 0; q < WT; ++q) acc[o][q] = fmaf(wv[o], xs[q + bp], acc[o][q]);
             }
         }
     };
     // full unrolling only while the straight-line code of both padding variants stays inside the
     // instruction cache (C = 6, OB = 6 fully unrolled: 41 % of the stall samples were instruction fetch)
-    if constexpr (CT > 0 && CT * KH * KW * OB * WT <= 1000) {
+    if constexpr (CT > 0 && CT * KH * KW * OB * WT * RB <= 1000) {
 #pragma unroll
         for (int cin = 0; cin < CT; ++cin) body(cin);
     } else {
@@ -192,22 +227,26 @@ __device__ __forceinline__ void conv_sub(const float* __restrict__ xt, const flo
         for (int cin = 0; cin < Cn; ++cin) body(cin);
     }
 #pragma unroll
-    for (int o = 0; o < OB; ++o) {
-        const int oc = ob * OB + o;
-        if (oc < C) {
-            float* yp = yt + oc * HW;
-            if constexpr (WT == 4) {
-                *reinterpret_cast<float4*>(yp) = make_float4(acc[o][0], acc[o][1], acc[o][2], acc[o][3]);
-            } else if constexpr (WT == 2) {
-                *reinterpret_cast<float2*>(yp) = make_float2(acc[o][0], acc[o][1]);
-            } else {
-                yp[0] = acc[o][0];
+    for (int rb = 0; rb < RB; ++rb) {
+        if (RB > 1 && h + rb >= H) break;
+#pragma unroll
+        for (int o = 0; o < OB; ++o) {
+            const int oc = ob * OB + o;
+            if (oc < C) {
+                float* yp = yt + oc * HW + rb * W;
+                if constexpr (WT == 4) {
+                    *reinterpret_cast<float4*>(yp) = make_float4(acc[rb][o][0], acc[rb][o][1], acc[rb][o][2], acc[rb][o][3]);
+                } else if constexpr (WT == 2) {
+                    *reinterpret_cast<float2*>(yp) = make_float2(acc[rb][o][0], acc[rb][o][1]);
+                } else {
+                    yp[0] = acc[rb][o][0];
+                }
             }
         }
     }
 }
 
-template <int CT, int OB, int WT, int KH, int KW>
+template <int CT, int OB, int WT, int KH, int KW, int RB = 1>
 __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kernel(const ConvArgs a) {
     constexpr int OBP = ObPad<OB>::value;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -322,7 +361,7 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kern
 
     // ---- consumers --------------------------------------------------------------------------------
     const int nob = CT > 0 ? (CT + OB - 1) / OB : a.nob;
-    const int sub_per_tile = nob * H * a.nstrip;
+    const int sub_per_tile = nob * a.HR * a.nstrip;
     if (a.prepared) mbar_wait(wbar, 0);
     long k = 0;
     for (long chunk = blockIdx.x; chunk < a.n_chunks; chunk += gridDim.x, ++k) {
@@ -353,7 +392,7 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kern
             const int strip = (int)(r - q * a.nstrip);
             r = q;
             q = fastdiv(r, a.m_h);
-            const int h = (int)(r - q * H);
+            const int h = (int)(r - q * a.HR) * RB;
             r = q;
             q = CT > 0 ? r / (unsigned)nob : fastdiv(r, a.m_nob);
             const int ob = (int)(r - q * nob);
@@ -361,8 +400,8 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kern
             const int w0 = strip * WT;
             const float* xt = buf + t * a.tile_floats;
             float* yt = a.y + ((long)(n0 + t) * s.G + g) * a.tile_floats + h * W + w0;
-            if (right) conv_sub<CT, OB, WT, KH, KW, true>(xt, zrow, wg, yt, C, H, W, HW, h, w0, r0, ob, nob);
-            else conv_sub<CT, OB, WT, KH, KW, false>(xt, zrow, wg, yt, C, H, W, HW, h, w0, r0, ob, nob);
+            if (right) conv_sub<CT, OB, WT, KH, KW, true, RB>(xt, zrow, wg, yt, C, H, W, HW, h, w0, r0, ob, nob);
+            else conv_sub<CT, OB, WT, KH, KW, false, RB>(xt, zrow, wg, yt, C, H, W, HW, h, w0, r0, ob, nob);
         }
         if (threadIdx.x == 0) dbg_mark(a.dbg, 3);
         if (a.bulk) {
@@ -374,8 +413,20 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kern
     }
 }
 
+// the row-blocked variant exists for the shapes the host planner may select it for (conv_rb_supported)
+constexpr bool rb2_instantiated(int CT, int OB, int WT, int KH) { return CT >= 1 && CT <= 3 && OB == CT && WT == 4 && KH == 3; }
+
 template <int CT, int OB, int WT, int KH, int KW>
 int launch_inst(const ConvArgs& a, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+    if constexpr (rb2_instantiated(CT, OB, WT, KH)) {
+        if (a.RB == 2) {
+            auto kern2 = conv_cta_kernel<CT, OB, WT, KH, KW, 2>;
+            cudaError_t e2 = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e2 != cudaSuccess) return (int)e2;
+            return launch_kernel(kern2, grid, threads, smem, st, a);
+        }
+    }
+    if (a.RB != 1) return FINC_E_UNSUPPORTED;
     auto kern = conv_cta_kernel<CT, OB, WT, KH, KW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

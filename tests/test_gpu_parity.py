@@ -100,6 +100,10 @@ ORACLE_CASES = [
     (2, 4, 3, 1, 1, 3, 3, (0, 1, 2, 3)),      # 1x1 image
     (2, 3, 2, 3, 2, 5, 5, (3, 0, 1)),         # kernel larger than the image, G=3
     (300, 4, 3, 8, 8, 3, 3, (0, 1, 2, 3)),    # many items per warp: exercises the pipeline
+    (700, 4, 3, 7, 8, 3, 3, (0, 1, 2, 3)),    # odd H, batch large enough for the row-blocked conv variant
+    (900, 4, 2, 5, 4, 3, 3, (3, 2, 1, 0)),
+    (1500, 4, 1, 3, 12, 3, 3, (0, 1, 2, 3)),
+    (6000, 4, 3, 16, 16, 3, 3, (0, 1, 2, 3)),  # CIFAR L0 at a batch that selects it (2 rows per sub-item)
 ]
 
 

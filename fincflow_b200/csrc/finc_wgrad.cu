@@ -515,7 +515,8 @@ size_t wgrad_workspace_floats(const Shape& s) {
     Plan p{}, q{};
     size_t f = 0;
     if (make_plan(s, &p)) f = partial_floats(s, p);
-    if (make_plan(s, &q, 4)) f = f > partial_floats(s, q) ? f : partial_floats(s, q);
+    for (int div : {2, 4, 8})
+        if (make_plan(s, &q, div)) f = f > partial_floats(s, q) ? f : partial_floats(s, q);
     return kCounterBytes / 4 + f;
 }
 
@@ -523,7 +524,8 @@ int launch_wgrad_fast(const float* dz, const float* x, float* dw, float* workspa
                       unsigned flags, cudaStream_t st, bool* handled) {
     *handled = false;
     Plan p{};
-    if (!make_plan(s, &p, (flags & FINC_FLAG_QUARTER_GPU) ? 4 : 1)) return 0;
+    static const int quarter_div = getenv("FINC_WG_DIV") ? atoi(getenv("FINC_WG_DIV")) : 4;  // experiment knob
+    if (!make_plan(s, &p, (flags & FINC_FLAG_QUARTER_GPU) ? quarter_div : 1)) return 0;
     if (ws_floats < kCounterBytes / 4 + partial_floats(s, p)) return FINC_E_WORKSPACE;
     {
         static const bool dbg_plan = getenv("FINC_WG_DEBUG") != nullptr;

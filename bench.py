@@ -177,7 +177,7 @@ def fp32_peak():
 
 def kernel_detail(torch, _native, dev, peak):
     """each kernel family alone at the three level shapes: batch 256 (the workload) and a
-    batch large enough to stream from HBM; L2 flushed before every timed launch.  The roofline
+    batch large enough to stream from HBM; per-launch time of a CUDA graph of 8 launches.  The roofline
     time of a launch is max(algorithmic bytes / HBM peak, flops / fp32 FFMA peak): Cq = 3 is
     HBM-bound (6.75 flop/B), Cq >= 6 is bound by the fp32 pipe."""
     from fincflow_b200.fastflow import FastFlowUnit
@@ -214,17 +214,28 @@ def kernel_detail(torch, _native, dev, peak):
                     k_roof = max(nbytes / peak / 1e3, k_flops / ffma / 1e6)
                 else:
                     k_flops, k_roof, k_bound = flops, t_roof_us, bound
-                for _ in range(3):
-                    fn()
+                # a CUDA graph of CHAIN launches (what the step replays), L2 flushed before each replay;
+                # at batch 256 the launches of a chain find their operands in L2, as inside the step
+                CHAIN = 8
+                side = torch.cuda.Stream(dev)
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        fn()
+                torch.cuda.synchronize(dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for _ in range(CHAIN):
+                        fn()
                 ts = []
-                for _ in range(7):
+                for _ in range(5):
                     flush.zero_()
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
-                    fn()
+                    g.replay()
                     e1.record()
                     e1.synchronize()
-                    ts.append(e0.elapsed_time(e1))
+                    ts.append(e0.elapsed_time(e1) / CHAIN)
+                del g
                 us = 1e3 * statistics.median(ts)
                 out.append({"kernel": name, "shape": [B, CT, H, W], "us": round(us, 2),
                             "GBps": round(nbytes / us / 1e3, 1), "frac_of_hbm_peak": round(nbytes / us / 1e3 / peak, 3),

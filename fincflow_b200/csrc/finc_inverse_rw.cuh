@@ -7,7 +7,7 @@
 // store, one launch per unit) but the solve itself never touches shared memory for its
 // dependencies:
 //
-//   * lane = (stack q, sweep column j, part p).  The sweep is skewed -- at step s lane j solves
+//   * lane = (part p, stack q, sweep column j), column fastest.  The sweep is skewed -- at step s lane j solves
 //     stacked row s-j -- so the pixel to the LEFT (row r, column j-1) was finished by lane j-1 one
 //     step ago and the pixel ABOVE (row r-1, column j) by this very lane.  Every input of the
 //     recurrence therefore arrives either from the lane's own registers or by ONE shuffle from
@@ -155,9 +155,13 @@ __global__ void __launch_bounds__(Cfg<C, KH, KW, P>::MAXW * 32, 1) inverse_rw_ke
     }
     if (threadIdx.x == 0) dbg_mark(a.dbg, 1);
 
-    const int p = lane % P;
-    const int j = (lane / P) % a.WP;   // sweep column
-    const int q = lane / (P * a.WP);   // stack inside the item
+    // lane = (p * QMAX + q) * WP + j: the part index is the SLOW one, so the 8 lanes of a 128-bit
+    // shared-memory phase read the same weight vector (with p fastest every LDS.128 of the weight
+    // table cost 4 wavefronts and the C = 12 kernel was bound by shared-memory bandwidth)
+    constexpr int LP = 32 / P;         // lanes per part
+    const int p = lane / LP;
+    const int j = lane % a.WP;         // sweep column
+    const int q = (lane % LP) / a.WP;  // stack inside the item
     const bool col_on = j < W && q < NSTK;
 
     long k = 0;
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(Cfg<C, KH, KW, P>::MAXW * 32, 1) inverse_rw_ke
 #pragma unroll
                 for (int kw = KW - 1; kw >= 1; --kw)
 #pragma unroll
-                    for (int il = 0; il < CL; ++il) sh[kw - 1][il] = __shfl_up_sync(0xffffffffu, win[kw - 1][sp][il], P);
+                    for (int il = 0; il < CL; ++il) sh[kw - 1][il] = __shfl_up_sync(0xffffffffu, win[kw - 1][sp][il], 1);
                 // (2) z of the next step's pixel travels while this one is solved
                 float* nptr = ptr;
                 int nhn = hn;
@@ -307,7 +311,7 @@ __global__ void __launch_bounds__(Cfg<C, KH, KW, P>::MAXW * 32, 1) inverse_rw_ke
                 // (6) the P partial sums of the pixel meet
                 if constexpr (P > 1) {
 #pragma unroll
-                    for (int off = 1; off < P; off <<= 1)
+                    for (int off = LP; off < 32; off <<= 1)
 #pragma unroll
                         for (int o = 0; o < C; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
                 }

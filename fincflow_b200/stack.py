@@ -154,11 +154,16 @@ class HotPathRunner:
     N_SIDE = int(os.environ.get("FINC_NSIDE", "6"))
 
     def __init__(self, stack: FincStack, batch: int, device, slots=1, lr=1e-3, host_io=False,
-                 process_group=None, use_graphs=True, use_prepared=True, fused_collective=True):
+                 process_group=None, use_graphs=True, use_prepared=True, fused_collective=True,
+                 device_latents=False):
         self.stack, self.B, self.device = stack, batch, torch.device(device)
         self.pg = process_group
         self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)
         self.host_io, self.use_graphs = host_io, use_graphs
+        # sampling latents z ~ N(0, I): drawn on the device inside the sampling graph, like the
+        # reference's model.sample -> base_distribution.sample (train/experiment.py:327-337), instead of
+        # travelling from the host
+        self.device_latents = device_latents
         self.grad = torch.zeros_like(stack.flat.data)
         self.fused_collective = False
         if self.world > 1 and fused_collective:
@@ -244,7 +249,8 @@ class HotPathRunner:
         """host -> device: this step's data batch (x) and sampling latents (z) of every level"""
         for li in range(len(self.stack.levels)):
             s.acts[li][0].copy_(s.x_host[li], non_blocking=True)
-            s.zin[li].copy_(s.z_host[li], non_blocking=True)
+            if not self.device_latents:
+                s.zin[li].copy_(s.z_host[li], non_blocking=True)
 
     def _copy_out(self, s):
         """device -> host: per-sample log-likelihoods and the generated samples of every level"""
@@ -305,6 +311,8 @@ class HotPathRunner:
     def _inverse(self, s):
         st = self.stack
         for li, lv in enumerate(st.levels):
+            if self.device_latents:
+                s.zin[li].normal_()
             src, cur = s.zin[li], 0
             for u in reversed(range(lv.n_units)):
                 _native.inverse(src, out=s.samp[li][cur], **self._w(li, u, _native.PREP_INVERSE))

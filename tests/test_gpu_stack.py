@@ -135,6 +135,34 @@ def test_host_io_pipeline_over_slots():
                 assert rel_err(x.cpu().numpy(), s.samp_host[li].numpy()) <= 1e-5
 
 
+def test_device_latents_sampling():
+    """device_latents=True: z ~ N(0, I) is drawn inside the sampling graph (reference: model.sample ->
+    base_distribution.sample on the device); the samples invert the latents that were drawn"""
+    from fincflow_b200.stack import FincStack, HotPathRunner
+
+    torch.manual_seed(4)
+    B = 64
+    lv = _small_levels()
+    stack = FincStack(lv).cuda()
+    runner = HotPathRunner(stack, B, "cuda", slots=1, lr=0.0, host_io=True, device_latents=True)
+    s = runner.slots[0]
+    for li in range(len(lv)):
+        s.x_host[li].normal_()
+    runner.prepare()
+    drawn = []
+    for _ in range(2):
+        runner.step(0)
+        runner.drain()
+        torch.cuda.synchronize()
+        drawn.append([z.clone() for z in s.zin])
+        with torch.no_grad():
+            for li in range(len(lv)):
+                z, _ = stack.forward(s.samp_host[li].cuda(), li)
+                assert rel_err(z.cpu().numpy(), s.zin[li].cpu().numpy()) <= 1e-5
+                assert abs(float(s.zin[li].mean())) < 0.05 and abs(float(s.zin[li].std()) - 1.0) < 0.05
+    assert not torch.equal(drawn[0][0], drawn[1][0])   # a fresh draw per replay
+
+
 def test_reference_cpu_path_twin_agrees():
     """bench.py's reference arm computes the same step as the GPU runner"""
     from fincflow_b200.stack import FincStack, HotPathRunner, LevelSpec

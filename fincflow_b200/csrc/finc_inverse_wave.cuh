@@ -141,8 +141,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
         if (threadIdx.x == 0) dbg_mark(a.dbg, 1);
     }
 
-    const int jj = lane / P;       // column slot
-    const int p = lane - jj * P;   // part
+    // lane = p * CB + jj: the part index is the slow one, so the lanes of a 128-bit shared-memory
+    // phase read the same weight vector (see finc_inverse_rw.cuh)
+    const int p = lane / CB;       // part
+    const int jj = lane - p * CB;  // column slot
     const int ncb = (W + CB - 1) / CB;
 
     // Taps in sweep coordinates (kh, kw) != (0,0).  NEAR taps (0,1) and (1,0) read pixels of the
@@ -317,7 +319,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) inverse_wave_kernel(const W
                         fma_row(acc, xa[m][i], nwp[m] + i * CPP, WN_REG ? &wn[WN_REG ? m : 0][WN_REG ? i : 0][0] : nullptr);
                 if constexpr (P > 1) {
 #pragma unroll
-                    for (int off = 1; off < P; off <<= 1)
+                    for (int off = CB; off < 32; off <<= 1)
 #pragma unroll
                         for (int o = 0; o < C; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
                 }

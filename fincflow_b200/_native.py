@@ -37,6 +37,7 @@ SYMBOLS = (
     "finc_backward_weight_f32", "finc_inverse_f32", "finc_apply_grad_mask_f32", "finc_logdet_f32",
     "finc_gaussian_logp_f32", "finc_debug_timestamps", "finc_prepared_weights_bytes", "finc_prepare_weights_f32",
     "finc_squeeze_f32", "finc_unsqueeze_f32", "finc_adam_step_f32", "finc_allreduce_adam_f32", "finc_affine1x1_f32",
+    "finc_affine1x1_backward_weight_workspace_bytes", "finc_affine1x1_backward_weight_f32",
 )
 
 _lib = None
@@ -84,6 +85,10 @@ def load():
     lib.finc_unsqueeze_f32.argtypes = [p, p, i, i, i, i, p]
     lib.finc_affine1x1_f32.restype = i
     lib.finc_affine1x1_f32.argtypes = [p, p, p, p, i, i, ctypes.c_long, p]
+    lib.finc_affine1x1_backward_weight_workspace_bytes.restype = sz
+    lib.finc_affine1x1_backward_weight_workspace_bytes.argtypes = [i, i, ctypes.c_long]
+    lib.finc_affine1x1_backward_weight_f32.restype = i
+    lib.finc_affine1x1_backward_weight_f32.argtypes = [p, p, p, p, p, sz, i, i, ctypes.c_long, p]
     lib.finc_prepared_weights_bytes.restype = sz
     lib.finc_prepared_weights_bytes.argtypes = [i] + dims
     lib.finc_prepare_weights_f32.restype = i
@@ -345,6 +350,25 @@ def affine1x1(x, A, bias=None, out=None):
     _check(load().finc_affine1x1_f32(x.data_ptr(), A.data_ptr(), 0 if bias is None else bias.data_ptr(), y.data_ptr(),
                                      B, C, HW, _stream(x)), "finc_affine1x1_f32")
     return y
+
+
+def affine1x1_backward_weight(dy, x, want_bias=True):
+    """(dA [C,C], dbias [C] or None) of y = A x + b over all pixels (autograd of ActNorm + Conv1x1)"""
+    dy = _prep(dy, "dy")
+    x = _prep(x, "x")
+    _bind_device(x)
+    B, C = x.shape[0], x.shape[1]
+    HW = 1
+    for d in x.shape[2:]:
+        HW *= d
+    dA = torch.empty((C, C), dtype=torch.float32, device=x.device)
+    db = torch.empty(C, dtype=torch.float32, device=x.device) if want_bias else None
+    nbytes = load().finc_affine1x1_backward_weight_workspace_bytes(B, C, HW)
+    ws = torch.empty(max(nbytes, 64), dtype=torch.uint8, device=x.device)
+    _check(load().finc_affine1x1_backward_weight_f32(dy.data_ptr(), x.data_ptr(), dA.data_ptr(),
+                                                     0 if db is None else db.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                     B, C, HW, _stream(x)), "finc_affine1x1_backward_weight_f32", 2)
+    return dA, db
 
 
 def sm_count() -> int:

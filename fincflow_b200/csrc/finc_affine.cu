@@ -120,7 +120,199 @@ int dispatch_vec(int vec, const float* x, const float* A, const float* bias, flo
     return launch_inst<C, 1>(x, A, bias, y, B, HW, st);
 }
 
+// ---- weight gradient of the per-pixel affine map ------------------------------------------------
+//   dA[o, i] = sum_{n,p} dy[n, o, p] * x[n, i, p],   db[o] = sum_{n,p} dy[n, o, p]
+// A C x C outer-product accumulation over all B*HW pixels (the autograd of ActNorm + Conv1x1:
+// dW, dlog_scale and dtranslation follow from dA / db by the chain rule on the host).  CTAs stride
+// over tiles of PT pixels; a tile of x and dy is staged channel-major in shared memory, thread
+// (4x4 block of (o, i), pixel slice) accumulates 16 products per pixel from 128-bit loads; slices
+// meet in shared memory in fixed order, CTAs write partials, a second launch sums them in CTA order
+// (deterministic, no floating-point atomics).
+constexpr int kAwPT = 64;       // pixels per tile
+constexpr int kAwPitch = kAwPT + 4;
+constexpr int kAwRounds = 3;    // 4x4 blocks per thread: (C/4)^2 <= 3 * 256  <=>  C <= 108
+
+__global__ void __launch_bounds__(256) affine1x1_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                              float* __restrict__ partial, int C, long HW,
+                                                              long npix, long ntiles, int slices) {
+    extern __shared__ __align__(16) float sm[];
+    float* xs = sm;                       // [C][kAwPitch]
+    float* ds = sm + (size_t)C * kAwPitch;  // [C][kAwPitch]
+    const int nib = C >> 2, nblk = nib * nib;
+    const int tid = threadIdx.x;
+    float acc[kAwRounds][4][4];
+    float dsum[kAwRounds][4];
+#pragma unroll
+    for (int r = 0; r < kAwRounds; ++r)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            dsum[r][a] = 0.f;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[r][a][b] = 0.f;
+        }
+    // thread -> (block, slice) for round r: unit = tid + r * 256; block = unit / slices
+    const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x)) & 15) == 0;
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long P0 = tile * kAwPT;
+        __syncthreads();  // previous tile fully consumed
+        if (vec) {
+            for (int e = tid; e < C * (kAwPT / 4); e += blockDim.x) {
+                const int c = e / (kAwPT / 4), q = (e - c * (kAwPT / 4)) * 4;
+                const long P = P0 + q;
+                float4 vx = make_float4(0.f, 0.f, 0.f, 0.f), vd = vx;
+                if (P < npix) {
+                    const long n = P / HW, pp = P - n * HW;
+                    const long off = (n * C + c) * HW + pp;
+                    vx = __ldcs(reinterpret_cast<const float4*>(x + off));
+                    vd = __ldcs(reinterpret_cast<const float4*>(dy + off));
+                }
+                *reinterpret_cast<float4*>(xs + c * kAwPitch + q) = vx;
+                *reinterpret_cast<float4*>(ds + c * kAwPitch + q) = vd;
+            }
+        } else {
+            for (int e = tid; e < C * kAwPT; e += blockDim.x) {
+                const int c = e / kAwPT, q = e - c * kAwPT;
+                const long P = P0 + q;
+                float vx = 0.f, vd = 0.f;
+                if (P < npix) {
+                    const long n = P / HW, pp = P - n * HW;
+                    const long off = (n * C + c) * HW + pp;
+                    vx = x[off];
+                    vd = dy[off];
+                }
+                xs[c * kAwPitch + q] = vx;
+                ds[c * kAwPitch + q] = vd;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kAwRounds; ++r) {
+            const int unit = tid + r * 256;
+            const int blk = unit / slices, sl = unit - blk * slices;
+            if (blk < nblk) {
+                const int ob = blk / nib, ib = blk - ob * nib;
+                const float* dp = ds + (ob * 4) * kAwPitch;
+                const float* xp = xs + (ib * 4) * kAwPitch;
+                for (int q = sl * 4; q < kAwPT; q += slices * 4) {
+                    float4 d4[4], x4[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        d4[a] = *reinterpret_cast<const float4*>(dp + a * kAwPitch + q);
+                        x4[a] = *reinterpret_cast<const float4*>(xp + a * kAwPitch + q);
+                    }
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            acc[r][a][b] = fmaf(d4[a].x, x4[b].x, acc[r][a][b]);
+                            acc[r][a][b] = fmaf(d4[a].y, x4[b].y, acc[r][a][b]);
+                            acc[r][a][b] = fmaf(d4[a].z, x4[b].z, acc[r][a][b]);
+                            acc[r][a][b] = fmaf(d4[a].w, x4[b].w, acc[r][a][b]);
+                        }
+                        if (ib == 0) dsum[r][a] += (d4[a].x + d4[a].y) + (d4[a].z + d4[a].w);
+                    }
+                }
+            }
+        }
+    }
+    // slices of a block meet in shared memory in slice order, then the CTA writes its partial
+    __syncthreads();
+    float* part = sm;  // [C*C + C], the staging buffers are free now
+    for (int s_ = 0; s_ < slices; ++s_) {
+#pragma unroll
+        for (int r = 0; r < kAwRounds; ++r) {
+            const int unit = tid + r * 256;
+            const int blk = unit / slices, sl = unit - blk * slices;
+            if (blk < nblk && sl == s_) {
+                const int ob = blk / nib, ib = blk - ob * nib;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        float* dst = part + (ob * 4 + a) * C + ib * 4 + b;
+                        *dst = (s_ == 0 ? 0.f : *dst) + acc[r][a][b];
+                    }
+                    if (ib == 0) {
+                        float* dst = part + C * C + ob * 4 + a;
+                        *dst = (s_ == 0 ? 0.f : *dst) + dsum[r][a];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const int nout = C * C + C;
+    for (int e = tid; e < nout; e += blockDim.x) partial[(size_t)blockIdx.x * nout + e] = part[e];
+}
+
+__global__ void affine1x1_wgrad_finish_kernel(const float* __restrict__ partial, float* __restrict__ dA,
+                                              float* __restrict__ db, int C, int nctas) {
+    const int nout = C * C + C;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nout; e += gridDim.x * blockDim.x) {
+        float v = 0.f;
+        for (int c = 0; c < nctas; ++c) v += partial[(size_t)c * nout + e];
+        if (e < C * C) dA[e] = v;
+        else if (db != nullptr) db[e - C * C] = v;
+    }
+}
+
+// any C: one thread per output, fixed summation order
+__global__ void affine1x1_wgrad_generic_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                               float* __restrict__ dA, float* __restrict__ db, int B, int C, long HW) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= C * C + C) return;
+    const bool bias = e >= C * C;
+    const int o = bias ? e - C * C : e / C, i = bias ? 0 : e - o * C;
+    float v = 0.f;
+    for (int n = 0; n < B; ++n) {
+        const float* dp = dy + ((long)n * C + o) * HW;
+        const float* xp = x + ((long)n * C + i) * HW;
+        for (long p = 0; p < HW; ++p) v += bias ? dp[p] : dp[p] * xp[p];
+    }
+    if (!bias) dA[e] = v;
+    else if (db != nullptr) db[o] = v;
+}
+
+int affine_wgrad_ctas(int B, long HW) {
+    const long ntiles = ((long)B * HW + kAwPT - 1) / kAwPT;
+    const long cap = (long)sm_count_cached() * 2;
+    return (int)(ntiles < cap ? ntiles : cap);
+}
+
 }  // namespace
+
+size_t affine1x1_wgrad_workspace_floats(int B, int C, long HW) {
+    if (C % 4 != 0 || (C / 4) * (C / 4) > kAwRounds * 256) return 16;  // generic kernel: no partials
+    return (size_t)affine_wgrad_ctas(B, HW) * ((size_t)C * C + C) + 16;
+}
+
+int launch_affine1x1_wgrad(const float* dy, const float* x, float* dA, float* db, float* workspace, size_t ws_floats,
+                           int B, int C, long HW, cudaStream_t st) {
+    if (C % 4 != 0 || (C / 4) * (C / 4) > kAwRounds * 256) {
+        const int nout = C * C + C;
+        affine1x1_wgrad_generic_kernel<<<(nout + 127) / 128, 128, 0, st>>>(dy, x, dA, db, B, C, HW);
+        return (int)cudaGetLastError();
+    }
+    if (ws_floats < affine1x1_wgrad_workspace_floats(B, C, HW)) return FINC_E_WORKSPACE;
+    const int nblk = (C / 4) * (C / 4);
+    int slices = 256 / nblk;
+    if (slices < 1) slices = 1;
+    if (slices > kAwPT / 4) slices = kAwPT / 4;
+    const int nctas = affine_wgrad_ctas(B, HW);
+    const long npix = (long)B * HW;
+    const long ntiles = (npix + kAwPT - 1) / kAwPT;
+    size_t smem = (size_t)2 * C * kAwPitch * sizeof(float);
+    const size_t need_part = ((size_t)C * C + C) * sizeof(float);
+    if (smem < need_part) smem = need_part;
+    cudaError_t e = cudaFuncSetAttribute(affine1x1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    affine1x1_wgrad_kernel<<<nctas, 256, smem, st>>>(dy, x, workspace, C, HW, npix, ntiles, slices);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    const int nout = C * C + C;
+    affine1x1_wgrad_finish_kernel<<<(nout + 255) / 256, 256, 0, st>>>(workspace, dA, db, C, nctas);
+    return (int)cudaGetLastError();
+}
 
 int launch_affine1x1(const float* x, const float* A, const float* bias, float* y, int B, int C, long HW, cudaStream_t st) {
     // widest vector the layout allows: rows start at multiples of HW floats from 16-byte aligned bases

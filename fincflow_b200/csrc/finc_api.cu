@@ -243,6 +243,25 @@ int finc_affine1x1_f32(const float* x, const float* A, const float* bias, float*
     return launch_affine1x1(x, A, bias, y, B, C, HW, (cudaStream_t)stream);
 }
 
+size_t finc_affine1x1_backward_weight_workspace_bytes(int B, int C, long HW) {
+    if (B < 0 || C < 1 || C > 4096 || HW < 1) return 0;
+    return affine1x1_wgrad_workspace_floats(B, C, HW) * sizeof(float);
+}
+
+int finc_affine1x1_backward_weight_f32(const float* dy, const float* x, float* dA, float* dbias, void* workspace,
+                                       size_t workspace_bytes, int B, int C, long HW, void* stream) {
+    if (B < 0 || C < 1 || C > 4096 || HW < 1 || !dA) return FINC_E_BADARG;
+    if (B > 0 && (!dy || !x)) return FINC_E_BADARG;
+    if (B > 0 && !workspace) return FINC_E_WORKSPACE;
+    if (B == 0) {
+        cudaError_t e = cudaMemsetAsync(dA, 0, (size_t)C * C * sizeof(float), (cudaStream_t)stream);
+        if (e == cudaSuccess && dbias) e = cudaMemsetAsync(dbias, 0, (size_t)C * sizeof(float), (cudaStream_t)stream);
+        return (int)e;
+    }
+    return launch_affine1x1_wgrad(dy, x, dA, dbias, static_cast<float*>(workspace), workspace_bytes / sizeof(float), B, C, HW,
+                                  (cudaStream_t)stream);
+}
+
 size_t finc_prepared_weights_bytes(int kind, int B, int G, int C, int H, int W, int kH, int kW) {
     if (!shape_ok(B, G, C, H, W, kH, kW) || B < 1) return 0;
     const Shape s = mk(B, G, C, H, W, kH, kW, 0);

@@ -304,8 +304,8 @@ class GlowStep(_Chain):
 
 
 class _Affine1x1Fn(torch.autograd.Function):
-    """y = A x + b per pixel on finc_affine1x1_f32; backward-data = the same kernel with A^T.
-    The C x C weight gradient is a tiny GEMM over all pixels (library bmm, glue level)."""
+    """y = A x + b per pixel on finc_affine1x1_f32; backward-data = the same kernel with A^T;
+    dA = sum dy x^T and db = sum dy on finc_affine1x1_backward_weight_f32."""
 
     @staticmethod
     def forward(ctx, x, A, b):
@@ -321,10 +321,8 @@ class _Affine1x1Fn(torch.autograd.Function):
         dy = dy.contiguous()
         dx = _native.affine1x1(dy, A.t().contiguous()) if ctx.needs_input_grad[0] else None
         dA = db = None
-        if ctx.needs_input_grad[1]:
-            dA = torch.bmm(dy.flatten(2), x.flatten(2).transpose(1, 2)).sum(0)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy.sum(dim=(0, 2, 3))
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dA, db = _native.affine1x1_backward_weight(dy, x, want_bias=ctx.has_bias)
         return dx, dA, db
 
 

@@ -174,6 +174,16 @@ int finc_unsqueeze_f32(const float* x, float* y, int B, int C4, int H, int W, vo
 int finc_affine1x1_f32(const float* x, const float* A, const float* bias, float* y,
                        int B, int C, long HW, void* stream);
 
+/* Weight gradient of finc_affine1x1_f32 (deterministic, no floating-point atomics):
+ *   dA[o, i] = sum_{n,p} dy[n, o, p] * x[n, i, p]        dbias[o] = sum_{n,p} dy[n, o, p]   (dbias may be NULL)
+ * From these the host gets dW = dA diag(exp(-log_s)), dlog_s and dtranslation by the chain rule
+ * (autograd of ActNorm + Conv1x1, layers/actnorm.py:14-52, layers/conv1x1.py:18-43).  `workspace` must
+ * hold finc_affine1x1_backward_weight_workspace_bytes(B, C, HW) bytes of device memory. */
+size_t finc_affine1x1_backward_weight_workspace_bytes(int B, int C, long HW);
+int finc_affine1x1_backward_weight_f32(const float* dy, const float* x, float* dA, float* dbias,
+                                       void* workspace, size_t workspace_bytes,
+                                       int B, int C, long HW, void* stream);
+
 /* Prepared weight tables (optional fast path for fixed shapes, e.g. CUDA-graph replays).
  * The tiled kernels need the weights transposed / sweep-ordered in shared memory; by default
  * every launch re-stages them from the raw [G*C, C, kH, kW] tensor (~1-2 us).  A table prepared

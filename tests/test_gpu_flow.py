@@ -162,3 +162,26 @@ def test_fused_glow_step_equals_layerwise(actnorm):
     assert p0.keys() == p1.keys()
     for n in p0:
         assert rel_err(p1[n].cpu().numpy(), p0[n].cpu().numpy()) <= 2e-5, n
+
+
+@pytest.mark.parametrize("shape", [(256, 12, 16, 16), (37, 24, 8, 8), (300, 48, 4, 4), (9, 96, 4, 4), (64, 4, 14, 14), (33, 8, 7, 7),
+                                   (5, 10, 5, 5), (1, 12, 2, 2), (3000, 12, 16, 16)],
+                         ids=lambda s: "B{}C{}_{}x{}".format(*s))
+def test_affine1x1_backward_weight(shape):
+    """dA = sum dy x^T, db = sum dy (finc_affine1x1_backward_weight_f32) vs fp64; deterministic"""
+    from fincflow_b200 import _native
+
+    B, C, H, W = shape
+    gen = torch.Generator().manual_seed(B + C)
+    x = torch.randn(B, C, H, W, generator=gen)
+    dy = torch.randn(B, C, H, W, generator=gen)
+    want_A = torch.einsum("nop,nip->oi", dy.double().flatten(2), x.double().flatten(2))
+    want_b = dy.double().sum(dim=(0, 2, 3))
+    dA, db = _native.affine1x1_backward_weight(dy.cuda(), x.cuda())
+    scale = float(want_A.abs().max())
+    assert (dA.cpu().double() - want_A).abs().max().item() <= 2e-5 * max(scale, (B * H * W) ** 0.5)
+    assert (db.cpu().double() - want_b).abs().max().item() <= 2e-5 * max(float(want_b.abs().max()), (B * H * W) ** 0.5)
+    dA2, db2 = _native.affine1x1_backward_weight(dy.cuda(), x.cuda())
+    assert torch.equal(dA, dA2) and torch.equal(db, db2)
+    dA3, none = _native.affine1x1_backward_weight(dy.cuda(), x.cuda(), want_bias=False)
+    assert none is None and torch.equal(dA, dA3)

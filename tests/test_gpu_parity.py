@@ -380,3 +380,39 @@ def test_prepared_weight_tables_are_bit_identical(nat, shape):
                 assert torch.equal(fn(x, ws[u]), fn(x, None, prepared=tables[u], ksize=(k, k)))
     # shapes outside the tiled kernels report 0 bytes instead of a table
     assert nat.prepared_weights_bytes(nat.PREP_FORWARD, 4, 1, 5, 6, 6, 2, 3) == 0
+
+
+def _fuzz_cases(n, seed=20261018):
+    """random shapes over every dispatch family: channel counts in and out of the instantiated sets,
+    square and non-square images and kernels, 1..4 groups with random corner orders, ragged batches"""
+    rng = np.random.default_rng(seed)
+    cases = []
+    for _ in range(n):
+        C = int(rng.choice([1, 2, 3, 4, 5, 6, 7, 12, 24]))
+        G = int(rng.choice([1, 2, 3, 4]))
+        H = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 12, 14, 16, 20]))
+        W = int(rng.choice([1, 2, 3, 4, 6, 7, 8, 12, 14, 16, 32, 36]))
+        k = (3, 3) if rng.random() < 0.6 else [(5, 5), (2, 2), (1, 3), (3, 2), (4, 4)][int(rng.integers(5))]
+        if C * H * W > 4096:
+            H = max(1, 4096 // (C * W))
+        B = int(rng.choice([1, 2, 3, 5, 17, 64, 130, 600])) if C * H * W < 800 else int(rng.choice([1, 2, 3, 9, 33]))
+        orders = tuple(int(o) for o in rng.integers(0, 4, size=G))
+        cases.append((B, G, C, H, W, k[0], k[1], orders))
+    return cases
+
+
+@pytest.mark.parametrize("case", _fuzz_cases(48), ids=lambda c: "B{}G{}C{}_{}x{}_k{}x{}_o{}".format(*c[:7], "".join(map(str, c[7]))))
+def test_fuzz_against_oracle(nat, case):
+    """every kernel family on random shapes vs the oracle (same tolerances as the named cases)"""
+    B, G, C, H, W, kH, kW, orders = case
+    rng = np.random.default_rng(abs(hash(case[:7])) % (2**32))
+    w = np.concatenate([fo.init_weight(C, (kH, kW), o, rng) for o in orders], 0)
+    x = rng.normal(size=(B, G * C, H, W)).astype(np.float32)
+    dz = rng.normal(size=x.shape).astype(np.float32)
+    zs = rng.normal(size=x.shape).astype(np.float32)
+    r = run_all(nat, x, w, dz, zs, orders)
+    assert rel_err(r["z"], fo.forward(x, w, orders)) <= REL_TOL
+    assert rel_err(r["dx"], fo.backward_input(dz, w, orders)) <= REL_TOL
+    assert rel_err(r["dw"], fo.backward_weight(dz, x, (kH, kW), orders)) <= REL_TOL
+    assert rel_err(r["x_zs"], fo.inverse(zs, w, orders)) <= REL_TOL
+    assert np.abs(r["x_rt"] - x).max() <= RT_TOL

@@ -15,8 +15,6 @@ namespace {
 // (finc_conv_c<N>.cu).  Larger blocks are more FMA-efficient; smaller ones give a small batch
 // enough sub-items to occupy every SM.
 int pick_ob(int ct, int C, long rows_strips_per_tile, long tiles_per_cta) {
-    static const int table[][4] = {{0, 0, 0, 0}};
-    (void)table;
     int cands[5];
     int n = 0;
     switch (ct) {

@@ -416,3 +416,52 @@ def test_fuzz_against_oracle(nat, case):
     assert rel_err(r["dw"], fo.backward_weight(dz, x, (kH, kW), orders)) <= REL_TOL
     assert rel_err(r["x_zs"], fo.inverse(zs, w, orders)) <= REL_TOL
     assert np.abs(r["x_rt"] - x).max() <= RT_TOL
+
+
+@pytest.mark.parametrize("shape", [(37, 12, 16, 16, 3), (1031, 24, 8, 8, 3), (300, 48, 4, 4, 3), (9, 96, 4, 4, 5), (33, 8, 7, 7, 3),
+                                   (5, 12, 32, 32, 5), (2100, 12, 16, 16, 3), (3, 20, 6, 36, 3)],
+                         ids=lambda s: "B{}C{}_{}x{}_k{}".format(*s))
+def test_no_out_of_bounds_writes(nat, shape):
+    """every output lives inside a larger buffer filled with a sentinel: the kernels (TMA bulk stores,
+    vector stores, ragged last items) must leave the guard zones on both sides untouched"""
+    B, CT, H, W, k = shape
+    torch.manual_seed(B + CT)
+    from fincflow_b200.fastflow import FastFlowUnit
+
+    GUARD, SENT = 4096, 12345.678
+
+    def guarded(n):
+        buf = torch.full((n + 2 * GUARD,), SENT, device="cuda")
+        return buf, buf[GUARD:GUARD + n]
+
+    def check(buf, n, what):
+        assert bool((buf[:GUARD] == SENT).all()) and bool((buf[GUARD + n:] == SENT).all()), what
+
+    w = FastFlowUnit(CT, CT, (k, k)).weight.detach().cuda()
+    x = torch.randn(B, CT, H, W, device="cuda")
+    dz = torch.randn_like(x)
+    n = x.numel()
+    for name, fn in (("forward", lambda o: nat.forward(x, w, out=o, want_logdet=False)),
+                     ("backward_input", lambda o: nat.backward_input(dz, w, out=o)),
+                     ("inverse", lambda o: nat.inverse(x, w, out=o)),
+                     ("inverse_wave", lambda o: nat.inverse(x, w, out=o, flags=nat.FLAG_WAVE_SMEM)),
+                     ("inverse_generic", lambda o: nat.inverse(x, w, out=o, flags=nat.FLAG_GENERIC_TILED))):
+        buf, view = guarded(n)
+        fn(view.view_as(x))
+        torch.cuda.synchronize()
+        check(buf, n, name)
+        assert not bool((view == SENT).any()), name + ": unwritten output"
+    buf, view = guarded(w.numel())
+    nat.backward_weight(dz, x, (k, k), out=view.view_as(w))
+    torch.cuda.synchronize()
+    check(buf, w.numel(), "backward_weight")
+    A = torch.linalg.qr(torch.randn(CT, CT, device="cuda"))[0].contiguous()
+    buf, view = guarded(n)
+    nat.affine1x1(x, A, torch.randn(CT, device="cuda"), out=view.view_as(x))
+    torch.cuda.synchronize()
+    check(buf, n, "affine1x1")
+    if H % 2 == 0 and W % 2 == 0:
+        buf, view = guarded(n)
+        nat.squeeze(x, out=view.view(B, 4 * CT, H // 2, W // 2))
+        torch.cuda.synchronize()
+        check(buf, n, "squeeze")

@@ -33,6 +33,11 @@ int pick_ob(int ct, int C, long rows_strips_per_tile, long tiles_per_cta) {
             }
     }
     int best = cands[n - 1];
+    if (const char* e = getenv("FINC_CONV_OB")) {  // experiment knob: force an instantiated block size
+        const int want = atoi(e);
+        for (int i = 0; i < n; ++i)
+            if (cands[i] == want) return want;
+    }
     for (int i = 0; i < n; ++i) {
         const long subs = tiles_per_cta * ((C + cands[i] - 1) / cands[i]) * rows_strips_per_tile;
         if (subs >= 384 || tiles_per_cta >= 64) return cands[i];

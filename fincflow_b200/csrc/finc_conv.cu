@@ -163,6 +163,10 @@ int launch_conv_fast(const float* x, const float* w, float* y, float* logdet, bo
     const long n_tiles = a.gsplit ? s.B : (long)s.B * s.G;
     long ctas_max = (a.gsplit ? sms / s.G : sms) / (sm_div > 1 ? sm_div : 1);  // (the weight-table layout does not depend on sm_div)
     if (ctas_max < 1) ctas_max = 1;
+    // experiment knob: FINC_CONV_SPLIT=k launches k smaller CTAs per SM (co-resident) instead of one
+    static const int cta_split = getenv("FINC_CONV_SPLIT") ? atoi(getenv("FINC_CONV_SPLIT")) : 1;
+    int max_cw = kMaxConsumerWarps;
+    if (cta_split > 1 && !a.gsplit) { ctas_max *= cta_split; max_cw = (kMaxConsumerWarps + 1) / cta_split - 1; }
     const long spread = (n_tiles + ctas_max - 1) / ctas_max;
     const int OB = wp.OB;
     a.nob = wp.nob;
@@ -185,7 +189,7 @@ int launch_conv_fast(const float* x, const float* w, float* y, float* logdet, bo
 
     // chunk: about one sub-item per consumer thread (512), at most 48 KB, and small enough that
     // every SM gets a chunk when the batch is small
-    int CH = (kMaxConsumerWarps * 32) / sub_per_tile;  // (rounded down: one pass of the consumer threads per chunk)
+    int CH = (max_cw * 32) / sub_per_tile;  // (rounded down: one pass of the consumer threads per chunk)
     if (CH < 1) CH = 1;
     while (CH > 1 && (long)CH * a.tile_floats * 4 > 48 * 1024) --CH;
     if (CH > spread) CH = (int)spread;
@@ -204,7 +208,7 @@ int launch_conv_fast(const float* x, const float* w, float* y, float* logdet, bo
     if (wk_bytes + S * stage_bytes + 256 > budget) return 0;
     a.S = S;
     int cw = (CH * sub_per_tile + 31) / 32;
-    if (cw > kMaxConsumerWarps) cw = kMaxConsumerWarps;
+    if (cw > max_cw) cw = max_cw;
     if (cw < 1) cw = 1;
     const size_t smem = wk_bytes + S * stage_bytes + 32 + (2 * S + 1) * 8 + 64;
     dim3 grid((unsigned)ctas, a.gsplit ? s.G : 1, 1);

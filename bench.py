@@ -199,12 +199,21 @@ def kernel_detail(torch, _native, dev, peak):
             ws = _native.new_workspace(_native.backward_weight_workspace_bytes(B, 4, CT // 4, H, W, KSIZE, KSIZE), dev)
             A1 = torch.linalg.qr(torch.randn(CT, CT, device=dev))[0].contiguous()
             b1 = torch.randn(CT, device=dev)
+            # prepared weight tables, as in the step (one table per kind, built once per weight update)
+            tabs = {}
+            for kind in (_native.PREP_FORWARD, _native.PREP_BACKWARD_INPUT, _native.PREP_INVERSE):
+                nb = _native.prepared_weights_bytes(kind, B, 4, CT // 4, H, W, KSIZE, KSIZE)
+                tabs[kind] = torch.empty((1, nb), dtype=torch.uint8, device=dev)
+                _native.prepare_weights(w[None], tabs[kind], kind, B, H, W)
+            kk = (KSIZE, KSIZE)
             fns = {
                 "affine1x1 (8f.1: ActNorm+Conv1x1 glue, HBM-bound)": lambda: _native.affine1x1(x, A1, b1, out=y),
-                "forward_logdet": lambda: _native.forward(x, w, out=y, want_logdet=False),
-                "backward_input": lambda: _native.backward_input(dz, w, out=y),
-                "backward_weight": lambda: _native.backward_weight(dz, x, (KSIZE, KSIZE), out=dw, workspace=ws),
-                "inverse": lambda: _native.inverse(x, w, out=y),
+                "forward_logdet": lambda: _native.forward(x, None, out=y, want_logdet=False,
+                                                          prepared=tabs[_native.PREP_FORWARD][0], ksize=kk),
+                "backward_input": lambda: _native.backward_input(dz, None, out=y,
+                                                                 prepared=tabs[_native.PREP_BACKWARD_INPUT][0], ksize=kk),
+                "backward_weight": lambda: _native.backward_weight(dz, x, kk, out=dw, workspace=ws),
+                "inverse": lambda: _native.inverse(x, None, out=y, prepared=tabs[_native.PREP_INVERSE][0], ksize=kk),
             }
             nbytes = 8 * x.numel()
             flops = 2.0 * B * H * W * CT * (CT // 4) * KSIZE * KSIZE

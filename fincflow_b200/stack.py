@@ -229,14 +229,27 @@ class HotPathRunner:
             self.fused_collective_error = repr(e)
 
     def _prepare_weights(self):
+        """one batched launch per (level, kind); the launches are independent of each other, so they
+        are fanned out over the side streams (fork / join on the current stream, graph-capturable)"""
         if self.tables is None:
             return
         st = self.stack
+        main = torch.cuda.current_stream(self.device)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        k = 0
         for li, lv in enumerate(st.levels):
             o = st.offsets[li][0]
             w_units = st.flat.detach()[o:o + lv.n_units * lv.unit_numel].view(lv.n_units, 4 * lv.cq, lv.cq, *lv.kernel_size)
             for kind in range(3):
-                _native.prepare_weights(w_units, self.tables[li][kind], kind, self.B, lv.height, lv.width)
+                side = self.side[k % self.N_SIDE]
+                if k < self.N_SIDE:
+                    side.wait_event(fork)
+                with torch.cuda.stream(side):
+                    _native.prepare_weights(w_units, self.tables[li][kind], kind, self.B, lv.height, lv.width)
+                k += 1
+        for side in self.side[:min(k, self.N_SIDE)]:
+            main.wait_stream(side)
 
     def _w(self, li, u, kind):
         """keyword arguments selecting the raw weights or the prepared table of unit (li, u)"""

@@ -124,7 +124,7 @@ class _Slot:
         self.acts, self.logdet, self.logp, self.dzs, self.samp, self.zin = [], [], [], [], [], []
         self.x_host, self.z_host, self.logp_host, self.samp_host = [], [], [], []
         self.sample_out = {}
-        self.ev_in, self.ev_computed, self.ev_out = (torch.cuda.Event() for _ in range(3))
+        self.ev_in, self.ev_computed, self.ev_out, self.ev_samp = (torch.cuda.Event() for _ in range(4))
         for lv in stack.levels:
             shp = (B, lv.channels, lv.height, lv.width)
             self.acts.append([torch.empty(shp, **f) for _ in range(lv.n_units + 1)])
@@ -155,7 +155,7 @@ class HotPathRunner:
 
     def __init__(self, stack: FincStack, batch: int, device, slots=1, lr=1e-3, host_io=False,
                  process_group=None, use_graphs=True, use_prepared=True, fused_collective=True,
-                 device_latents=False):
+                 device_latents=False, overlap_sampling=False):
         self.stack, self.B, self.device = stack, batch, torch.device(device)
         self.pg = process_group
         self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)
@@ -164,6 +164,12 @@ class HotPathRunner:
         # reference's model.sample -> base_distribution.sample (train/experiment.py:327-337), instead of
         # travelling from the host
         self.device_latents = device_latents
+        # overlap_sampling: the sampling pass (inverse phase) of step k runs on its own stream,
+        # concurrently with the forward / backward phases of step k+1 -- both only READ the weights
+        # produced by update k; update k+1 waits until that sampling pass has finished with the tables
+        self.overlap_sampling = overlap_sampling
+        self.samp_stream = torch.cuda.Stream(torch.device(device)) if overlap_sampling else None
+        self._ev_samp_prev = None
         self.grad = torch.zeros_like(stack.flat.data)
         self.fused_collective = False
         if self.world > 1 and fused_collective:
@@ -391,26 +397,56 @@ class HotPathRunner:
         this step's inputs (copy-in stream), the four compute phases (current stream) and the
         device->host copies of its results (copy-out stream) are ordered by events per slot, so
         the copies of step k+1 / k-1 travel while step k computes.  Results of `slot` are valid on
-        the host after `wait(slot)` (or `drain()`)."""
+        the host after `wait(slot)` (or `drain()`).
+
+        With overlap_sampling the last phase (the sampling pass) runs on a second stream next to the
+        forward / backward phases of the following step; phase events of that pass are recorded on its
+        own stream, so phase durations overlap and no longer add up to the step time."""
         n = len(self.PHASES)
         s = self.slots[slot]
         main = torch.cuda.current_stream(self.device)
         if self.host_io:
             self.copy_stream.wait_event(s.ev_computed)   # previous use of this slot has read its inputs
+            if self.overlap_sampling:
+                self.copy_stream.wait_event(s.ev_samp)
             with torch.cuda.stream(self.copy_stream):
                 self._replay_or_run(slot, "in", self._copy_in)
                 s.ev_in.record(self.copy_stream)
             main.wait_event(s.ev_in)
             main.wait_event(s.ev_out)                    # previous results of this slot have left the device
-        for p in range(n):
+        if not self.overlap_sampling:
+            for p in range(n):
+                if events is not None:
+                    events[p].record()
+                self.run_phase(slot, p)
             if events is not None:
-                events[p].record()
-            self.run_phase(slot, p)
-        if events is not None:
-            events[n].record()
+                events[n].record()
+        else:
+            samp = self.samp_stream
+            if self.host_io:
+                main.wait_event(s.ev_samp)               # (slot reuse: its previous sampling pass is done)
+            for p in range(n - 1):
+                if events is not None:
+                    events[p].record()
+                if p == n - 2 and self._ev_samp_prev is not None:
+                    main.wait_event(self._ev_samp_prev)  # the tables are rewritten by this phase
+                self.run_phase(slot, p)
+            ev_opt = torch.cuda.Event()
+            ev_opt.record(main)
+            samp.wait_event(ev_opt)
+            with torch.cuda.stream(samp):
+                if events is not None:
+                    events[n - 1].record()
+                self.run_phase(slot, n - 1)
+                if events is not None:
+                    events[n].record()
+                s.ev_samp.record(samp)
+            self._ev_samp_prev = s.ev_samp
         if self.host_io:
             s.ev_computed.record(main)
             self.copy_out_stream.wait_event(s.ev_computed)
+            if self.overlap_sampling:
+                self.copy_out_stream.wait_event(s.ev_samp)
             with torch.cuda.stream(self.copy_out_stream):
                 self._replay_or_run(slot, "out", self._copy_out)
                 s.ev_out.record(self.copy_out_stream)
@@ -430,7 +466,9 @@ class HotPathRunner:
     def drain(self):
         """make the current stream wait for every outstanding host copy (so that an event recorded
         after drain() covers the whole pipeline)"""
+        main = torch.cuda.current_stream(self.device)
+        if self.overlap_sampling:
+            main.wait_stream(self.samp_stream)
         if self.host_io:
-            main = torch.cuda.current_stream(self.device)
             main.wait_stream(self.copy_stream)
             main.wait_stream(self.copy_out_stream)

@@ -28,6 +28,7 @@ FLAG_PREPARED = 64
 FLAG_QUARTER_GPU = 128
 FLAG_HALF_GPU = 256
 FLAG_WAVE_SMEM = 512
+FLAG_TF32_1PASS = 1024
 PREP_FORWARD, PREP_BACKWARD_INPUT, PREP_INVERSE = 0, 1, 2
 
 # every symbol declared in include/fincflow_b200.h
@@ -38,6 +39,9 @@ SYMBOLS = (
     "finc_gaussian_logp_f32", "finc_debug_timestamps", "finc_prepared_weights_bytes", "finc_prepare_weights_f32",
     "finc_squeeze_f32", "finc_unsqueeze_f32", "finc_adam_step_f32", "finc_allreduce_adam_f32", "finc_affine1x1_f32",
     "finc_affine1x1_backward_weight_workspace_bytes", "finc_affine1x1_backward_weight_f32",
+    "finc_tc_conv_weights_bytes", "finc_tc_conv_prepare_weights_f32", "finc_tc_conv_nhwc_f32",
+    "finc_coupling_prepared_bytes", "finc_coupling_workspace_bytes", "finc_coupling_prepare_f32",
+    "finc_coupling_apply_f32",
 )
 
 _lib = None
@@ -93,6 +97,20 @@ def load():
     lib.finc_prepared_weights_bytes.argtypes = [i] + dims
     lib.finc_prepare_weights_f32.restype = i
     lib.finc_prepare_weights_f32.argtypes = [p, p, i, i, sz, sz, *dims, u, p]
+    lib.finc_tc_conv_weights_bytes.restype = sz
+    lib.finc_tc_conv_weights_bytes.argtypes = [i, i, i, i]
+    lib.finc_tc_conv_prepare_weights_f32.restype = i
+    lib.finc_tc_conv_prepare_weights_f32.argtypes = [p, p, i, i, i, i, p]
+    lib.finc_tc_conv_nhwc_f32.restype = i
+    lib.finc_tc_conv_nhwc_f32.argtypes = [p, p, p, p, p, i, i, i, i, i, i, i, u, p]
+    lib.finc_coupling_prepared_bytes.restype = sz
+    lib.finc_coupling_prepared_bytes.argtypes = [i, i]
+    lib.finc_coupling_workspace_bytes.restype = sz
+    lib.finc_coupling_workspace_bytes.argtypes = [i, i, i, i, i]
+    lib.finc_coupling_prepare_f32.restype = i
+    lib.finc_coupling_prepare_f32.argtypes = [p] * 7 + [ctypes.c_float, p, i, i, p]
+    lib.finc_coupling_apply_f32.restype = i
+    lib.finc_coupling_apply_f32.argtypes = [p, p, p, p, p, sz, i, i, i, i, i, i, u, p]
     for f in ("finc_set_device", "finc_forward_f32", "finc_backward_input_f32", "finc_backward_weight_f32",
               "finc_inverse_f32", "finc_apply_grad_mask_f32", "finc_logdet_f32", "finc_gaussian_logp_f32"):
         getattr(lib, f).restype = i
@@ -369,6 +387,83 @@ def affine1x1_backward_weight(dy, x, want_bias=True):
                                                      0 if db is None else db.data_ptr(), ws.data_ptr(), ws.numel(),
                                                      B, C, HW, _stream(x)), "finc_affine1x1_backward_weight_f32", 2)
     return dA, db
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core path (tcgen05 / TMEM / TMA tensor maps)
+# ---------------------------------------------------------------------------------------------
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def tc_conv_prepare_weights(w, mode=0):
+    """hi / lo TF32 split of an OIHW conv weight in the K-major layout of finc_tc_conv_nhwc_f32
+    (mode 0 = as is, 1 = im2col form of a 3x3, 2 = transposed + flipped for backward-data)"""
+    w = _prep(w, "weight")
+    _bind_device(w)
+    N, Cin, kh, kw = (int(v) for v in w.shape)
+    taps = kh * kw
+    nbytes = load().finc_tc_conv_weights_bytes(N, Cin, taps, mode)
+    if nbytes == 0:
+        raise FincNativeError(f"tc_conv_prepare_weights: unsupported weight shape {tuple(w.shape)}")
+    out = torch.empty(nbytes // 4, dtype=torch.float32, device=w.device)
+    _check(load().finc_tc_conv_prepare_weights_f32(w.data_ptr(), out.data_ptr(), N, Cin, taps, mode, _stream(w)),
+           "finc_tc_conv_prepare_weights_f32")
+    return out
+
+
+def tc_conv_nhwc(x, wprep, bias, Npad, taps, relu=False, relu_mask=None, flags=0, out=None):
+    """channels-last conv on the tensor cores: x [B,H,W,Cin_pad] -> y [B,H,W,Npad] (both padded to 32)"""
+    x = _prep(x, "x")
+    _bind_device(x)
+    B, H, W, Cp = (int(v) for v in x.shape)
+    y = torch.empty((B, H, W, Npad), dtype=torch.float32, device=x.device) if out is None else out
+    _check(load().finc_tc_conv_nhwc_f32(x.data_ptr(), wprep.data_ptr(), bias.data_ptr(),
+                                        None if relu_mask is None else relu_mask.data_ptr(), y.data_ptr(),
+                                        B, H, W, Cp, Npad, taps, int(relu), flags, _stream(x)), "finc_tc_conv_nhwc_f32")
+    return y
+
+
+def coupling_prepared_bytes(C, width) -> int:
+    """bytes of the prepared weight blob of one Coupling layer; 0 = not covered by the tensor-core path"""
+    return int(load().finc_coupling_prepared_bytes(C, width))
+
+
+def coupling_workspace_bytes(B, C, H, W, width) -> int:
+    return int(load().finc_coupling_workspace_bytes(B, C, H, W, width))
+
+
+def coupling_prepare(w1, b1, w2, b2, w3, b3, logs3, logscale_factor=3.0, out=None):
+    """weights of Coupling.net (layers/coupling.py:56-66) -> one prepared blob (uint8 tensor)"""
+    ts = [_prep(t, "coupling parameter") for t in (w1, b1, w2, b2, w3, b3, logs3)]
+    _bind_device(ts[0])
+    C, width = int(w3.shape[0]), int(w1.shape[0])
+    nbytes = coupling_prepared_bytes(C, width)
+    if nbytes == 0:
+        raise FincNativeError(f"coupling_prepare: C={C}, width={width} not covered by the tensor-core path")
+    blob = torch.empty(nbytes, dtype=torch.uint8, device=ts[0].device) if out is None else out
+    _check(load().finc_coupling_prepare_f32(*[t.data_ptr() for t in ts], float(logscale_factor), blob.data_ptr(),
+                                            C, width, _stream(ts[0])), "finc_coupling_prepare_f32", 4)
+    return blob
+
+
+def coupling_apply(x, blob, width, reverse=False, want_logdet=True, logdet_out=None, flags=0, out=None, workspace=None):
+    """Coupling.forward / .reverse (layers/coupling.py:85-99): y, logdet[B] (None for reverse)"""
+    x = _prep(x, "x")
+    _bind_device(x)
+    B, C, H, W = (int(v) for v in x.shape)
+    y = torch.empty_like(x) if out is None else out
+    nbytes = coupling_workspace_bytes(B, C, H, W, width)
+    if nbytes == 0:
+        raise FincNativeError(f"coupling_apply: shape {tuple(x.shape)}, width {width} not covered")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device) if workspace is None else workspace
+    logdet = None
+    if not reverse and (want_logdet or logdet_out is not None):
+        logdet = torch.empty(B, dtype=torch.float32, device=x.device) if logdet_out is None else logdet_out
+    _check(load().finc_coupling_apply_f32(x.data_ptr(), y.data_ptr(), None if logdet is None else logdet.data_ptr(),
+                                          blob.data_ptr(), ws.data_ptr(), ws.numel(), B, C, H, W, width, int(reverse),
+                                          flags, _stream(x)), "finc_coupling_apply_f32", 5)
+    return y, logdet
 
 
 def sm_count() -> int:

@@ -1,0 +1,357 @@
+// tc_api.cu -- host side of the tensor-core path: TMA tensor maps, weight preparation (hi / lo
+// TF32 split), im2col for the small-channel first convolution, and the extern "C" entry points
+// finc_tc_conv_* / finc_coupling_* declared in include/fincflow_b200.h.
+//
+// Reference layer: fastflow/layers/coupling.py:9-105 (Conv2dZero, Coupling) -- 3x3 C/2 -> width,
+// ReLU, 1x1 width -> width, ReLU, 3x3 width -> C (zero-init, * exp(3 logs)), then
+// log_s = 2 tanh(h[::2] / 2), t = h[1::2], z2 = x2 * exp(log_s) + t.
+#include "tc_host.cuh"
+
+#include <cudaTypedefs.h>
+
+namespace finc {
+namespace tc {
+
+int launch_igemm_nhwc_p1(int BN, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const Geom&, const EpiArgs&,
+                         cudaStream_t);
+int launch_igemm_nhwc_p3(int BN, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const Geom&, const EpiArgs&,
+                         cudaStream_t);
+int launch_igemm_coupling_p1(int BN, const CUtensorMap&, const CUtensorMap&, const Geom&, const EpiArgs&, cudaStream_t);
+int launch_igemm_coupling_p3(int BN, const CUtensorMap&, const CUtensorMap&, const Geom&, const EpiArgs&, cudaStream_t);
+
+int launch_igemm_nhwc(int BN, int npass, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const Geom& g,
+                      const EpiArgs& e, cudaStream_t st) {
+    return npass == 1 ? launch_igemm_nhwc_p1(BN, a, b, o, g, e, st) : launch_igemm_nhwc_p3(BN, a, b, o, g, e, st);
+}
+int launch_igemm_coupling(int BN, int npass, const CUtensorMap& a, const CUtensorMap& b, const Geom& g, const EpiArgs& e,
+                          cudaStream_t st) {
+    return npass == 1 ? launch_igemm_coupling_p1(BN, a, b, g, e, st) : launch_igemm_coupling_p3(BN, a, b, g, e, st);
+}
+
+// ---- tensor maps ------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+// channels-last activation [B, H, W, C] (C % 4 == 0), box = (32 channels, wb, hb, nb) pixels, 128-byte swizzle;
+// coordinates outside the tensor read as zero (= conv padding) and are dropped on stores
+static int map_nhwc(CUtensorMap* m, const float* base, int C, int W, int H, int B, int wb, int hb, int nb) {
+    auto enc = encoder();
+    if (enc == nullptr) return FINC_E_UNSUPPORTED;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)wb, (cuuint32_t)hb, (cuuint32_t)nb};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : FINC_E_BADARG;
+}
+// weight matrix [rows, K] row-major, box = (32, BN)
+static int map_weights(CUtensorMap* m, const float* base, long rows, int K, int BN) {
+    auto enc = encoder();
+    if (enc == nullptr) return FINC_E_UNSUPPORTED;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : FINC_E_BADARG;
+}
+
+static int pow2ceil(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+static Geom make_geom(int B, int H, int W, int taps, int Cpad, int Npad, int BN) {
+    Geom g;
+    g.W = W; g.H = H; g.B = B;
+    g.wb = pow2ceil(W) < kBM ? pow2ceil(W) : kBM;
+    g.hb = pow2ceil(H) < kBM / g.wb ? pow2ceil(H) : kBM / g.wb;
+    g.nb = kBM / (g.wb * g.hb);
+    g.tiles_w = (W + g.wb - 1) / g.wb;
+    g.tiles_h = (H + g.hb - 1) / g.hb;
+    g.tiles_n = (B + g.nb - 1) / g.nb;
+    g.taps = taps;
+    g.kb_per_tap = Cpad / kBK;
+    g.n_tiles = Npad / BN;
+    g.n_rows = Npad;
+    return g;
+}
+
+static int pick_bn_nhwc(int Npad) {
+    return Npad % 256 == 0 ? 256 : Npad % 128 == 0 ? 128 : Npad % 64 == 0 ? 64 : 32;
+}
+
+// ---- small kernels ----------------------------------------------------------------------------
+// out[part][tap][n][c] (Npad x Cpad per tap, zero padded), part 0 = tf32(w), part 1 = tf32(w - tf32(w)).
+//   mode 0: w is OIHW [N, Cin, kh, kw], taps = kh*kw, row n = output channel, c = input channel
+//   mode 1: im2col form of a 3x3 conv: ONE tap, c = tap9 * Cin + cin          (first coupling conv)
+//   mode 2: transposed + flipped (backward-data): row = input channel, c = output channel, tap -> taps-1-tap
+__global__ void split_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int N, int Cin, int taps,
+                                     int Npad, int Cpad, int mode) {
+    const int out_taps = mode == 1 ? 1 : taps;
+    const long per_part = (long)out_taps * Npad * Cpad;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < per_part; idx += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % Cpad);
+        const int n = (int)((idx / Cpad) % Npad);
+        const int tap = (int)(idx / ((long)Cpad * Npad));
+        float v = 0.f;
+        if (mode == 0) {
+            if (n < N && c < Cin) v = w[((long)n * Cin + c) * taps + tap];
+        } else if (mode == 1) {
+            if (n < N && c < taps * Cin) v = w[((long)n * Cin + c % Cin) * taps + c / Cin];
+        } else {
+            if (n < Cin && c < N) v = w[((long)c * Cin + n) * taps + (taps - 1 - tap)];
+        }
+        const float hi = tf32_rn(v);
+        out[idx] = hi;
+        out[per_part + idx] = tf32_rn(v - hi);
+    }
+}
+
+// A1[pixel][k] = x[n, k % Cin, h + (k / Cin) / 3 - 1, w + (k / Cin) % 3 - 1], zero outside the image and for
+// k >= 9 Cin; x is NCHW with `Ctot` channels of which the first Cin are read
+__global__ void im2col3x3_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int Ctot, int Cin, int H,
+                                 int W, int Kpad) {
+    const long total = (long)B * H * W * Kpad;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int k = (int)(idx % Kpad);
+        long p = idx / Kpad;
+        const int pw = (int)(p % W);
+        p /= W;
+        const int ph = (int)(p % H);
+        const int n = (int)(p / H);
+        float v = 0.f;
+        if (k < 9 * Cin) {
+            const int tap = k / Cin, c = k - tap * Cin;
+            const int hh = ph + tap / 3 - 1, ww = pw + tap % 3 - 1;
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(x + (((long)n * Ctot + c) * H + hh) * W + ww);
+        }
+        out[idx] = v;
+    }
+}
+
+// logdet[n] (+)= sum_p rowsum[n, p]  in a fixed order (deterministic)
+__global__ void rowsum_reduce_kernel(const float* __restrict__ rowsum, float* __restrict__ logdet, int HW,
+                                     int accumulate) {
+    __shared__ float red[128];
+    const int n = blockIdx.x;
+    float s = 0.f;
+    for (int p = threadIdx.x; p < HW; p += 128) s += rowsum[(long)n * HW + p];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) logdet[n] = (accumulate ? logdet[n] : 0.f) + red[0];
+}
+
+// bias / scale vectors of the zero-initialised last conv: scale = exp(logscale_factor * logs)
+__global__ void coupling_vectors_kernel(const float* __restrict__ b1, const float* __restrict__ b2,
+                                        const float* __restrict__ b3, const float* __restrict__ logs3, float factor,
+                                        float* __restrict__ o1, float* __restrict__ o2, float* __restrict__ o3,
+                                        float* __restrict__ s3, int width, int C, int N3pad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < width) {
+        o1[i] = b1[i];
+        o2[i] = b2[i];
+    }
+    if (i < N3pad) {
+        o3[i] = i < C ? b3[i] : 0.f;
+        s3[i] = i < C ? expf(factor * logs3[i]) : 0.f;
+    }
+}
+
+// ---- prepared coupling blob ----------------------------------------------------------------------
+struct CouplingLayout {
+    int C, width, Cin, K1pad, N3pad;
+    size_t w1, b1, w2, b2, w3, b3, s3, total;  // float offsets
+};
+static CouplingLayout coupling_layout(int C, int width) {
+    CouplingLayout L;
+    L.C = C; L.width = width; L.Cin = C / 2;
+    L.K1pad = round_up(9 * L.Cin, kBK);
+    L.N3pad = round_up(C, 16);
+    size_t o = 32;  // header
+    L.w1 = o; o += (size_t)2 * width * L.K1pad;
+    L.b1 = o; o += round_up(width, 32);
+    L.w2 = o; o += (size_t)2 * width * width;
+    L.b2 = o; o += round_up(width, 32);
+    L.w3 = o; o += (size_t)2 * 9 * L.N3pad * width;
+    L.b3 = o; o += round_up(L.N3pad, 32);
+    L.s3 = o; o += round_up(L.N3pad, 32);
+    L.total = o;
+    return L;
+}
+static bool coupling_supported(int C, int width) {
+    if (C < 2 || (C & 1) || width < 32 || width % 32 != 0 || width > 4096) return false;
+    const int n3 = round_up(C, 16);
+    return n3 == 16 || n3 == 32 || n3 == 48 || n3 == 64 || n3 == 96;
+}
+
+struct Workspace {
+    size_t a1, h1, h2, rowsum, total;  // float offsets
+};
+static Workspace coupling_workspace(int B, int C, int H, int W, int width) {
+    const CouplingLayout L = coupling_layout(C, width);
+    const size_t np = (size_t)B * H * W;
+    Workspace w;
+    size_t o = 0;
+    w.a1 = o; o += np * L.K1pad;
+    w.h1 = o; o += np * width;
+    w.h2 = o; o += np * width;
+    w.rowsum = o; o += (np + 31) / 32 * 32;
+    w.total = o;
+    return w;
+}
+
+static int grid_for(long total, int threads) {
+    long b = (total + threads - 1) / threads;
+    const long cap = (long)sm_count_cached() * 16;
+    return (int)(b < 1 ? 1 : b > cap ? cap : b);
+}
+
+// one channels-last convolution on the tensor cores
+static int conv_nhwc(const float* x, const float* wsplit, const float* bias, const float* mask, float* y, int B, int H,
+                     int W, int Cpad, int Npad, int taps, int relu, int npass, cudaStream_t st) {
+    const int BN = pick_bn_nhwc(Npad);
+    const Geom g = make_geom(B, H, W, taps, Cpad, Npad, BN);
+    CUtensorMap mA, mB, mO;
+    int rc = map_nhwc(&mA, x, Cpad, W, H, B, g.wb, g.hb, g.nb);
+    if (rc) return rc;
+    rc = map_weights(&mB, wsplit, (long)2 * taps * Npad, Cpad, BN);
+    if (rc) return rc;
+    rc = map_nhwc(&mO, y, Npad, W, H, B, g.wb, g.hb, g.nb);
+    if (rc) return rc;
+    EpiArgs e{};
+    e.bias = bias;
+    e.relu = relu;
+    e.mask = mask;
+    return launch_igemm_nhwc(BN, npass, mA, mB, mO, g, e, st);
+}
+
+}  // namespace tc
+}  // namespace finc
+
+using namespace finc;
+using namespace finc::tc;
+
+extern "C" {
+
+size_t finc_tc_conv_weights_bytes(int N, int Cin, int taps, int mode) {
+    if (N < 1 || Cin < 1 || (taps != 1 && taps != 9)) return 0;
+    const int rows = mode == 2 ? Cin : N, cols = mode == 2 ? N : mode == 1 ? taps * Cin : Cin;
+    const int out_taps = mode == 1 ? 1 : taps;
+    return (size_t)2 * out_taps * round_up(rows, 32) * round_up(cols, kBK) * sizeof(float);
+}
+
+int finc_tc_conv_prepare_weights_f32(const float* w, void* out, int N, int Cin, int taps, int mode, void* stream) {
+    if (!w || !out || N < 1 || Cin < 1 || (taps != 1 && taps != 9) || mode < 0 || mode > 2) return FINC_E_BADARG;
+    const int rows = mode == 2 ? Cin : N, cols = mode == 2 ? N : mode == 1 ? taps * Cin : Cin;
+    const int Npad = round_up(rows, 32), Cpad = round_up(cols, kBK);
+    const long per_part = (long)(mode == 1 ? 1 : taps) * Npad * Cpad;
+    split_weights_kernel<<<grid_for(per_part, 256), 256, 0, (cudaStream_t)stream>>>(w, (float*)out, N, Cin, taps, Npad,
+                                                                                    Cpad, mode);
+    return (int)cudaGetLastError();
+}
+
+int finc_tc_conv_nhwc_f32(const float* x, const void* wprep, const float* bias, const float* relu_mask, float* y, int B,
+                          int H, int W, int Cin_pad, int Npad, int taps, int relu, unsigned flags, void* stream) {
+    if (!x || !wprep || !bias || !y || B < 1 || H < 1 || W < 1 || Cin_pad < kBK || Cin_pad % kBK || Npad < 32 ||
+        Npad % 32 || (taps != 1 && taps != 9))
+        return FINC_E_BADARG;
+    return conv_nhwc(x, (const float*)wprep, bias, relu_mask, y, B, H, W, Cin_pad, Npad, taps, relu,
+                     (flags & FINC_FLAG_TF32_1PASS) ? 1 : 3, (cudaStream_t)stream);
+}
+
+size_t finc_coupling_prepared_bytes(int C, int width) {
+    return coupling_supported(C, width) ? coupling_layout(C, width).total * sizeof(float) : 0;
+}
+
+size_t finc_coupling_workspace_bytes(int B, int C, int H, int W, int width) {
+    if (!coupling_supported(C, width) || B < 1 || H < 1 || W < 1) return 0;
+    return coupling_workspace(B, C, H, W, width).total * sizeof(float);
+}
+
+int finc_coupling_prepare_f32(const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                              const float* b3, const float* logs3, float logscale_factor, void* prepared, int C,
+                              int width, void* stream) {
+    if (!w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !logs3 || !prepared) return FINC_E_BADARG;
+    if (!coupling_supported(C, width)) return FINC_E_UNSUPPORTED;
+    const CouplingLayout L = coupling_layout(C, width);
+    float* p = (float*)prepared;
+    cudaStream_t st = (cudaStream_t)stream;
+    split_weights_kernel<<<grid_for((long)width * L.K1pad, 256), 256, 0, st>>>(w1, p + L.w1, width, L.Cin, 9, width,
+                                                                               L.K1pad, 1);
+    split_weights_kernel<<<grid_for((long)width * width, 256), 256, 0, st>>>(w2, p + L.w2, width, width, 1, width, width,
+                                                                             0);
+    split_weights_kernel<<<grid_for((long)9 * L.N3pad * width, 256), 256, 0, st>>>(w3, p + L.w3, C, width, 9, L.N3pad,
+                                                                                   width, 0);
+    const int nv = width > L.N3pad ? width : L.N3pad;
+    coupling_vectors_kernel<<<(nv + 127) / 128, 128, 0, st>>>(b1, b2, b3, logs3, logscale_factor, p + L.b1, p + L.b2,
+                                                              p + L.b3, p + L.s3, width, C, L.N3pad);
+    return (int)cudaGetLastError();
+}
+
+int finc_coupling_apply_f32(const float* x, float* y, float* logdet, const void* prepared, void* workspace,
+                            size_t workspace_bytes, int B, int C, int H, int W, int width, int reverse, unsigned flags,
+                            void* stream) {
+    if (!x || !y || !prepared || !workspace || B < 1 || H < 1 || W < 1) return FINC_E_BADARG;
+    if (!coupling_supported(C, width)) return FINC_E_UNSUPPORTED;
+    const CouplingLayout L = coupling_layout(C, width);
+    const Workspace ws = coupling_workspace(B, C, H, W, width);
+    if (workspace_bytes < ws.total * sizeof(float)) return FINC_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* p = (const float*)prepared;
+    float* wsp = (float*)workspace;
+    const int npass = (flags & FINC_FLAG_TF32_1PASS) ? 1 : 3;
+    const long np = (long)B * H * W;
+
+    im2col3x3_kernel<<<grid_for(np * L.K1pad, 256), 256, 0, st>>>(x, wsp + ws.a1, B, C, L.Cin, H, W, L.K1pad);
+    int rc = (int)cudaGetLastError();
+    if (rc) return rc;
+    rc = conv_nhwc(wsp + ws.a1, p + L.w1, p + L.b1, nullptr, wsp + ws.h1, B, H, W, L.K1pad, width, 1, 1, npass, st);
+    if (rc) return rc;
+    rc = conv_nhwc(wsp + ws.h1, p + L.w2, p + L.b2, nullptr, wsp + ws.h2, B, H, W, width, width, 1, 1, npass, st);
+    if (rc) return rc;
+
+    const Geom g = make_geom(B, H, W, 9, width, L.N3pad, L.N3pad);
+    CUtensorMap mA, mB;
+    rc = map_nhwc(&mA, wsp + ws.h2, width, W, H, B, g.wb, g.hb, g.nb);
+    if (rc) return rc;
+    rc = map_weights(&mB, p + L.w3, (long)2 * 9 * L.N3pad, width, L.N3pad);
+    if (rc) return rc;
+    EpiArgs e{};
+    e.bias = p + L.b3;
+    e.scale = p + L.s3;
+    e.x = x;
+    e.y = y;
+    e.rowsum = (logdet != nullptr && !reverse) ? wsp + ws.rowsum : nullptr;
+    e.C = C;
+    e.reverse = reverse;
+    rc = launch_igemm_coupling(L.N3pad, npass, mA, mB, g, e, st);
+    if (rc) return rc;
+    if (e.rowsum != nullptr) {
+        rowsum_reduce_kernel<<<B, 128, 0, st>>>(wsp + ws.rowsum, logdet, H * W,
+                                               (flags & FINC_FLAG_LOGDET_ACCUMULATE) ? 1 : 0);
+        rc = (int)cudaGetLastError();
+    }
+    return rc;
+}
+
+}  // extern "C"

@@ -55,6 +55,7 @@ extern "C" {
 #define FINC_FLAG_HALF_GPU 256u /* forward / backward_input: use at most half of the SMs (leaves room for concurrent launches on other streams) */
 #define FINC_FLAG_WAVE_SMEM 512u /* inverse: skip the register-window kernel, use the shared-memory wavefront kernel (testing) */
 #define FINC_FLAG_LOGDET_ACCUMULATE 8u /* forward: logdet[n] += ... (FlowSequential's `logdet += layer_logdet`) */
+#define FINC_FLAG_TF32_1PASS 1024u /* tensor-core entry points: single-pass TF32 products (PyTorch's default conv precision, ~5e-4) instead of the fp32-accurate 3xTF32 split */
 
 /* error codes (negative); positive return values are cudaError_t */
 #define FINC_OK 0
@@ -204,6 +205,42 @@ int finc_prepare_weights_f32(const float* w, void* prepared, int kind, int n_uni
                              size_t w_stride_floats, size_t prepared_stride_bytes,
                              int B, int G, int C, int H, int W, int kH, int kW,
                              unsigned orders, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tensor-core path (tcgen05.mma kind::tf32, accumulators in TMEM, TMA tensor maps).
+ *
+ * Channels-last convolution  y[b,h,w,n] = act(sum_{tap,c} x[b, h+dy, w+dx, c] * Wt[tap][n][c] + bias[n])
+ * for taps = 1 (1x1) or 9 (3x3, zero padding 1).  x is [B,H,W,Cin_pad] and y [B,H,W,Npad] fp32 with
+ * Cin_pad % 32 == 0 and Npad % 32 == 0 (pad channels are zero).  Products are 3xTF32
+ * (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, fp32-accurate) unless FINC_FLAG_TF32_1PASS.  `relu_mask`
+ * (channels-last [B,H,W,Npad], may be NULL) zeroes outputs where mask <= 0 (ReLU backward).
+ * Weights are prepared once per update by finc_tc_conv_prepare_weights_f32:
+ *   mode 0: w = OIHW [N, Cin, kh, kw]                      -> rows n (padded to 32), K = Cin (padded to 32)
+ *   mode 1: im2col form of a 3x3 conv: one tap, K = 9*Cin  (pairs with a [B,H,W,9*Cin] patch tensor)
+ *   mode 2: transposed + flipped (the backward-data convolution): rows = Cin, K = N
+ * Replaces the nn.Conv2d (cuDNN) calls of the Coupling network, fastflow/layers/coupling.py:56-66. */
+size_t finc_tc_conv_weights_bytes(int N, int Cin, int taps, int mode);
+int finc_tc_conv_prepare_weights_f32(const float* w, void* prepared, int N, int Cin, int taps, int mode, void* stream);
+int finc_tc_conv_nhwc_f32(const float* x, const void* prepared, const float* bias, const float* relu_mask, float* y,
+                          int B, int H, int W, int Cin_pad, int Npad, int taps, int relu, unsigned flags, void* stream);
+
+/* Affine coupling layer (fastflow/layers/coupling.py:44-105) in four launches:
+ *   h = Conv2dZero(relu(conv1x1(relu(conv3x3(x[:, :C/2])))));  log_s = 2 tanh(h[:, ::2] / 2);  t = h[:, 1::2]
+ *   forward:  y = cat(x1, x2 * exp(log_s) + t),   logdet[n] (+)= sum log_s        (Coupling.forward)
+ *   reverse:  y = cat(x1, (x2 - t) * exp(-log_s))                               (Coupling.reverse)
+ * x, y: NCHW [B, C, H, W] (y == x allowed); the hidden activations stay channels-last in `workspace`.
+ * `prepared` = finc_coupling_prepare_f32(net.0.weight [width,C/2,3,3], net.0.bias, net.2.weight
+ * [width,width,1,1], net.2.bias, net.4.weight [C,width,3,3], net.4.bias, net.4.logs, logscale_factor).
+ * finc_coupling_prepared_bytes returns 0 for shapes the path does not cover
+ * (C even, round_up(C,16) in {16,32,48,64,96}, width % 32 == 0). */
+size_t finc_coupling_prepared_bytes(int C, int width);
+size_t finc_coupling_workspace_bytes(int B, int C, int H, int W, int width);
+int finc_coupling_prepare_f32(const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                              const float* b3, const float* logs3, float logscale_factor, void* prepared,
+                              int C, int width, void* stream);
+int finc_coupling_apply_f32(const float* x, float* y, float* logdet, const void* prepared, void* workspace,
+                            size_t workspace_bytes, int B, int C, int H, int W, int width, int reverse,
+                            unsigned flags, void* stream);
 
 /* Debug aid, inactive unless the environment has FINC_DEBUG_TS=1: the tiled kernels then record
  * per-CTA %globaltimer marks (8 slots per CTA); this call synchronises the device and copies them. */

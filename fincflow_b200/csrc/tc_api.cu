@@ -93,7 +93,7 @@ static Geom make_geom(int B, int H, int W, int taps, int Cpad, int Npad, int BN)
 }
 
 static int pick_bn_nhwc(int Npad) {
-    return Npad % 256 == 0 ? 256 : Npad % 128 == 0 ? 128 : Npad % 64 == 0 ? 64 : 32;
+    return Npad % 128 == 0 ? 128 : Npad % 64 == 0 ? 64 : 32;
 }
 
 // ---- small kernels ----------------------------------------------------------------------------

@@ -3,20 +3,36 @@
 //   D[pixel, n] = sum_{tap, c} X[pixel + tap, c] * Wt[tap][n][c]        (1x1 or 3x3 / pad 1)
 //
 // for channels-last fp32 activations X [B, H, W, Cin] and weights pre-arranged as K-major rows
-// [part][tap][n][c].  The contraction runs on tcgen05.mma kind::tf32 with accumulators in TMEM.
-// fp32 parity with an fp32 reference ("not TF32") comes from the 3xTF32
-// split  a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo  (a_hi = tf32(a), a_lo = tf32(a - a_hi)):
-// weights are split once on the device (`part` 0 = hi, 1 = lo); activation tiles are split in
-// shared memory by four transform warps between the TMA load and the MMA.  NPASS = 1 is the plain
-// single-pass TF32 product (PyTorch's default conv precision) for callers that ask for it.
+// [part][tap][n][c].  The products run on tcgen05.mma kind::tf32 with accumulators in TMEM.
+//
+// fp32 parity ("not TF32") needs two things:
+//  (1) 3xTF32 split products  a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  (a_hi = tf32(a),
+//      a_lo = tf32(a - a_hi)): weights are split once on the device (`part` 0 = hi, 1 = lo);
+//      activation tiles are split in shared memory by four transform warps between the TMA load
+//      and the MMA.  NPASS = 1 is the plain single-pass TF32 product (PyTorch's default conv
+//      precision) for callers that ask for it.
+//  (2) short tensor-core accumulation chains.  The tensor core adds into its fp32 accumulator with
+//      truncation, so the error of a long chain grows linearly with K (measured on B200: 3.4e-6 at
+//      K = 512, 2.6e-5 at K = 4608 where cuDNN's fp32 is at 7e-7).  Here the MMAs of one GROUP
+//      (FLUSH k-blocks of 32) accumulate into a fresh TMEM partial and the epilogue warps add the
+//      partials into fp32 registers with round-to-nearest (two-level accumulation).  The K slices
+//      of a k-block go to KSPLIT independent accumulators: back-to-back MMAs into ONE small
+//      accumulator serialise on its TMEM read-modify-write (~100 cycles each at N = 16).
+//
+//  (3) the A operand (activations) comes from TENSOR MEMORY, not shared memory.  Measured on the
+//      shared-memory-operand version (profiles/r2_tc_v2_ss_mode.md): the shared-memory data pipe was
+//      saturated (tensor-core operand fetch 47 % + the split warps' loads / stores 40 % + TMA writes)
+//      with the tensor pipe at 26 %; an MMA took ~2 cycles per operand wavefront.  The split warps
+//      read every activation element anyway, so they now write hi / lo straight into TMEM
+//      (tcgen05.st) and the tensor core fetches only the weight tile from shared memory.
 //
 // Warp roles of one persistent CTA (320 threads, one CTA per SM):
 //   warp 0      TMA producer: 4-D box loads of the activation tile (out-of-image taps are zero
 //               filled by the TMA unit = the conv padding) + 2-D loads of the weight tile
 //   warp 1      TMEM allocation, single-thread tcgen05.mma issue, tcgen05.commit -> mbarriers
-//   warps 2-5   hi/lo split of the activation tile in shared memory (NPASS = 3 only)
-//   warps 6-9   epilogue: tcgen05.ld -> bias / ReLU / coupling math -> TMA store or NCHW stores
-// Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+//   warps 2-5   activation tile shared memory -> registers -> hi / lo split -> TMEM (tcgen05.st)
+//   warps 6-9   accumulate partials (tcgen05.ld + FADD), then bias / ReLU / coupling math and
+//               TMA store (channels-last) or NCHW stores
 #pragma once
 
 #include "tc_common.cuh"
@@ -64,14 +80,25 @@ template <int BN, int NPASS>
 struct Cfg {
     static constexpr int kBBytes = BN * kBK * 4;
     static constexpr int kParts = NPASS == 3 ? 2 : 1;
-    static constexpr int kStageBytes = kParts * (kABytes + kBBytes);
-    static constexpr int kAvail = kSmemLimit - 2 * kStagingBytes - 2048;
+    static constexpr int kStageBytes = kABytes + kParts * kBBytes;   // raw activation tile + weight tile(s)
+    static constexpr int kAvail = kSmemLimit - 2 * kStagingBytes - 2048 - 1024;
     static constexpr int kStagesRaw = kAvail / kStageBytes;
-    static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+    static constexpr int kStages = kStagesRaw > 4 ? 4 : kStagesRaw;   // 4 activation stages fit in TMEM
     static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStagingBytes + 2048;
-    static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+    // two-level accumulation
+    static constexpr int kFlush = NPASS == 3 ? 1 : 4;                  // k-blocks per TMEM partial
+    static constexpr int kSplit = BN <= 32 ? 4 : BN <= 64 ? 2 : 1;     // independent accumulators per partial
+    static constexpr int kPartCols = kSplit * BN;
+    static constexpr int kACols = kParts * kBK;                        // TMEM columns of one activation stage
+    static constexpr int kNPartRaw = (512 - kStages * kACols) / kPartCols;
+    static constexpr int kNPart = kNPartRaw > 4 ? 4 : kNPartRaw;       // ring depth
+    static constexpr int kAColBase = kNPart * kPartCols;               // activation stages sit behind the partials
+    static constexpr int kUsedCols = kAColBase + kStages * kACols;
+    static constexpr int kTmemCols = kUsedCols <= 32 ? 32 : kUsedCols <= 64 ? 64 : kUsedCols <= 128 ? 128 : kUsedCols <= 256 ? 256 : 512;
     static_assert(kStages >= 2, "pipeline needs two stages");
-    static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M = 128");
+    static_assert(kNPart >= 2, "partial ring needs two buffers");
+    static_assert(kUsedCols <= 512, "TMEM columns");
+    static_assert(BN % 16 == 0 && BN >= 16 && BN <= 128, "UMMA N for M = 128; 128 running sums per epilogue thread");
 };
 
 struct TileCoord {
@@ -95,25 +122,25 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
              const __grid_constant__ CUtensorMap mapOut, const Geom g, const EpiArgs e) {
     using C = Cfg<BN, NPASS>;
     constexpr int S = C::kStages;
+    constexpr int NP = C::kNPart;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* staging = smem + S * C::kStageBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
-    uint64_t* full = bars;             // [S]  TMA bytes landed
-    uint64_t* empty = bars + S;        // [S]  MMAs that read the stage have completed
-    uint64_t* xf = bars + 2 * S;       // [S]  activation tile split into hi / lo
-    uint64_t* acc_full = bars + 3 * S; // [2]  accumulator stage complete
-    uint64_t* acc_empty = acc_full + 2;  // [2]  accumulator stage drained by the epilogue
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* full = bars;               // [S]  TMA bytes landed
+    uint64_t* empty = bars + S;          // [S]  MMAs that read the stage have completed
+    uint64_t* xf = bars + 2 * S;         // [S]  activation tile split into hi / lo
+    uint64_t* part_full = bars + 3 * S;  // [NP] partial accumulator complete
+    uint64_t* part_empty = part_full + NP;  // [NP] partial added into the running sums
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(part_empty + NP);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles_total = g.tiles_w * g.tiles_h * g.tiles_n * g.n_tiles;
     const int kblocks = g.taps * g.kb_per_tap;
 
-    auto a_hi = [&](int s) { return smem + s * C::kStageBytes; };
-    auto a_lo = [&](int s) { return smem + s * C::kStageBytes + kABytes; };
-    auto b_hi = [&](int s) { return smem + s * C::kStageBytes + C::kParts * kABytes; };
-    auto b_lo = [&](int s) { return smem + s * C::kStageBytes + C::kParts * kABytes + C::kBBytes; };
+    auto a_raw = [&](int s) { return smem + s * C::kStageBytes; };
+    auto b_hi = [&](int s) { return smem + s * C::kStageBytes + kABytes; };
+    auto b_lo = [&](int s) { return smem + s * C::kStageBytes + kABytes + C::kBBytes; };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA);
@@ -124,9 +151,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             mbar_init(&empty[s], 1);
             mbar_init(&xf[s], kXfThreads);
         }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], kEpiThreads);
+        for (int i = 0; i < NP; ++i) {
+            mbar_init(&part_full[i], 1);
+            mbar_init(&part_empty[i], kEpiThreads);
         }
         fence_mbar_init();
     }
@@ -149,7 +176,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                         const int s = it % S;
                         mbar_wait_long(&empty[s], ((it / S) & 1) ^ 1);
                         mbar_arrive_expect_tx(&full[s], kABytes + C::kParts * C::kBBytes);
-                        tma_load_4d(a_hi(s), &mapA, &full[s], kb * kBK, t.w0 + dx, t.h0 + dy, t.n0);
+                        tma_load_4d(a_raw(s), &mapA, &full[s], kb * kBK, t.w0 + dx, t.h0 + dy, t.n0);
                         tma_load_2d(b_hi(s), &mapB, &full[s], kb * kBK, tap * g.n_rows + t.ncol0);
                         if (NPASS == 3)
                             tma_load_2d(b_lo(s), &mapB, &full[s], kb * kBK, (g.taps + tap) * g.n_rows + t.ncol0);
@@ -161,90 +188,122 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
-            uint32_t it = 0, j = 0;
-            for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++j) {
-                const uint32_t as = j & 1;
-                mbar_wait_long(&acc_empty[as], ((j >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
-                for (int kblk = 0; kblk < kblocks; ++kblk, ++it) {
-                    const int s = it % S;
-                    const uint32_t ph = (it / S) & 1;
-                    mbar_wait_long(&full[s], ph);
-                    if (NPASS == 3) mbar_wait_long(&xf[s], ph);
-                    tc_fence_after();
-                    const uint64_t da_hi = umma_desc_k_sw128(a_hi(s)), db_hi = umma_desc_k_sw128(b_hi(s));
-                    const uint64_t da_lo = umma_desc_k_sw128(a_lo(s)), db_lo = umma_desc_k_sw128(b_lo(s));
-#pragma unroll
-                    for (int k = 0; k < kBK / kUmmaK; ++k) {
-                        const uint64_t adv = (uint64_t)(k * kUmmaK * 4 >> 4);  // 32 bytes per K step inside the swizzle row
-                        if (NPASS == 3) {
-                            // small terms first, the dominant product last
-                            umma_tf32(d_tmem, da_lo + adv, db_hi + adv, idesc, (kblk | k) != 0);
-                            umma_tf32(d_tmem, da_hi + adv, db_lo + adv, idesc, 1);
-                            umma_tf32(d_tmem, da_hi + adv, db_hi + adv, idesc, 1);
-                        } else {
-                            umma_tf32(d_tmem, da_hi + adv, db_hi + adv, idesc, (kblk | k) != 0);
-                        }
-                    }
-                    umma_commit(&empty[s]);
-                }
-                umma_commit(&acc_full[as]);
-            }
-        }
-    } else if (warp < 6) {
-        // ===================== hi / lo split of the activation tile =====================
-        if (NPASS == 3) {
-            const int t = threadIdx.x - 64;
-            uint32_t it = 0;
+            uint32_t it = 0, gq = 0;   // k-block counter, group (= partial) counter
             for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
                 for (int kblk = 0; kblk < kblocks; ++kblk, ++it) {
                     const int s = it % S;
-                    mbar_wait_long(&full[s], (it / S) & 1);
-                    float4* hi = reinterpret_cast<float4*>(a_hi(s));
-                    float4* lo = reinterpret_cast<float4*>(a_lo(s));
-#pragma unroll
-                    for (int i = 0; i < kABytes / 16 / kXfThreads; ++i) {
-                        const int idx = i * kXfThreads + t;   // elementwise: the swizzle does not matter
-                        const float4 v = hi[idx];
-                        float4 h, l;
-                        h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
-                        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-                        hi[idx] = h;
-                        lo[idx] = l;
+                    const uint32_t ph = (it / S) & 1;
+                    const int in_group = kblk % C::kFlush;
+                    const uint32_t p = gq % NP;
+                    if (in_group == 0) {
+                        mbar_wait_long(&part_empty[p], ((gq / NP) & 1) ^ 1);
+                        tc_fence_after();
                     }
-                    fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
-                    mbar_arrive(&xf[s]);
+                    const uint32_t d_tmem = tmem_base + p * C::kPartCols;
+                    mbar_wait_long(&full[s], ph);   // weight tile landed
+                    mbar_wait_long(&xf[s], ph);     // activation tile split into TMEM
+                    tc_fence_after();
+                    const uint64_t db_hi = umma_desc_k_sw128(b_hi(s)), db_lo = umma_desc_k_sw128(b_lo(s));
+                    const uint32_t ta_hi = tmem_base + C::kAColBase + s * C::kACols, ta_lo = ta_hi + kBK;
+                    // pass-major order: the three products of one K slice land in the same accumulator
+                    // kSplit MMAs apart
+#pragma unroll
+                    for (int pass = 0; pass < NPASS; ++pass) {
+#pragma unroll
+                        for (int k = 0; k < kBK / kUmmaK; ++k) {
+                            const uint64_t adv = (uint64_t)(k * kUmmaK * 4 >> 4);  // 32 bytes per K step inside the swizzle row
+                            const uint32_t d = d_tmem + (k % C::kSplit) * BN;
+                            // first write of this accumulator in this group?
+                            const uint32_t acc = (in_group != 0 || pass != 0 || k >= C::kSplit) ? 1u : 0u;
+                            // small terms first, the dominant product last
+                            const uint32_t ta = ((NPASS == 3 && pass == 0) ? ta_lo : ta_hi) + k * kUmmaK;
+                            const uint64_t db = (NPASS == 3 && pass == 1) ? db_lo : db_hi;
+                            umma_tf32_ts(d, ta, db + adv, idesc, acc);
+                        }
+                    }
+                    umma_commit(&empty[s]);
+                    if (in_group == C::kFlush - 1 || kblk == kblocks - 1) {
+                        umma_commit(&part_full[p]);
+                        ++gq;
+                    }
                 }
             }
         }
+    } else if (warp < 6) {
+        // ===================== activation tile: shared memory -> hi / lo -> TMEM =====================
+        // thread = one tile row (pixel): its 128 bytes sit in 8 swizzled 16-byte chunks; eight consecutive
+        // rows read eight different chunk slots, so the loads are bank-conflict free
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + C::kAColBase;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+            for (int kblk = 0; kblk < kblocks; ++kblk, ++it) {
+                const int s = it % S;
+                mbar_wait_long(&full[s], (it / S) & 1);   // also: the MMAs that read TMEM stage s have completed
+                const uint8_t* src = a_raw(s) + row * 128;
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 v = *reinterpret_cast<const float4*>(src + ((j ^ (row & 7)) << 4));
+                    const float h0 = tf32_rn(v.x), h1 = tf32_rn(v.y), h2 = tf32_rn(v.z), h3 = tf32_rn(v.w);
+                    hi[4 * j + 0] = __float_as_uint(h0); hi[4 * j + 1] = __float_as_uint(h1);
+                    hi[4 * j + 2] = __float_as_uint(h2); hi[4 * j + 3] = __float_as_uint(h3);
+                    if (NPASS == 3) {
+                        lo[4 * j + 0] = __float_as_uint(v.x - h0); lo[4 * j + 1] = __float_as_uint(v.y - h1);
+                        lo[4 * j + 2] = __float_as_uint(v.z - h2); lo[4 * j + 3] = __float_as_uint(v.w - h3);
+                    }
+                }
+                tmem_st_x32(lane_addr + s * C::kACols, hi);
+                if (NPASS == 3) tmem_st_x32(lane_addr + s * C::kACols + kBK, lo);
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(&xf[s]);
+            }
+        }
     } else {
-        // ===================== epilogue =====================
+        // ===================== accumulate partials + epilogue =====================
         const int q = warp & 3;              // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;       // accumulator row = pixel inside the tile
         const int te = threadIdx.x - 192;
-        uint32_t j = 0, cc = 0;
-        for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++j) {
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int groups = (kblocks + C::kFlush - 1) / C::kFlush;
+        uint32_t gq = 0, cc = 0;
+        for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
             const TileCoord t = tile_coord(g, tile, BN);
-            const uint32_t as = j & 1;
-            mbar_wait_long(&acc_full[as], (j >> 1) & 1);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
-            if (EPI == EPI_NHWC) {
-                // pixel of this row (the ReLU-backward mask needs it; the TMA store clips by itself)
-                const int pw = t.w0 + row % g.wb, phh = t.h0 + (row / g.wb) % g.hb, pn = t.n0 + row / (g.wb * g.hb);
-                const bool valid = pw < g.W && phh < g.H && pn < g.B;
-                const size_t pix = ((size_t)pn * g.H + phh) * g.W + pw;
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c, ++cc) {
-                    uint32_t v[2][16];
-                    tmem_ld_x16(taddr + c * 32, v[0]);
-                    tmem_ld_x16(taddr + c * 32 + 16, v[1]);
+            float acc[BN];
+#pragma unroll
+            for (int i = 0; i < BN; ++i) acc[i] = 0.f;
+            for (int gi = 0; gi < groups; ++gi, ++gq) {
+                const uint32_t p = gq % NP;
+                mbar_wait_long(&part_full[p], (gq / NP) & 1);
+                tc_fence_after();
+                const uint32_t taddr = lane_addr + p * C::kPartCols;
+                // a group shorter than one k-block's slices cannot happen: every accumulator of the
+                // partial is written by the first k-block of the group
+#pragma unroll
+                for (int c = 0; c < BN / 16; ++c) {
+                    uint32_t v[C::kSplit][16];
+#pragma unroll
+                    for (int sp = 0; sp < C::kSplit; ++sp) tmem_ld_x16(taddr + sp * BN + c * 16, v[sp]);
                     tmem_wait_ld();
-                    if (c == BN / 32 - 1) {
-                        tc_fence_before();
-                        mbar_arrive(&acc_empty[as]);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float sum = __uint_as_float(v[0][i]);
+#pragma unroll
+                        for (int sp = 1; sp < C::kSplit; ++sp) sum += __uint_as_float(v[sp][i]);
+                        acc[c * 16 + i] += sum;
                     }
+                }
+                tc_fence_before();
+                mbar_arrive(&part_empty[p]);
+            }
+            const int pw = t.w0 + row % g.wb, phh = t.h0 + (row / g.wb) % g.hb, pn = t.n0 + row / (g.wb * g.hb);
+            const bool valid = pw < g.W && phh < g.H && pn < g.B;
+            if (EPI == EPI_NHWC) {
+                const size_t pix = ((size_t)pn * g.H + phh) * g.W + pw;
+#pragma unroll
+                for (int c = 0; c < BN / 32; ++c, ++cc) {
                     uint8_t* buf = staging + (cc & 1) * kStagingBytes;
                     if (te == 0) bulk_wait_read<1>();   // the store that last read `buf` has finished reading
                     named_bar_sync(1, kEpiThreads);
@@ -253,10 +312,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                     for (int jj = 0; jj < 8; ++jj) {
                         const float4 bv = __ldg(reinterpret_cast<const float4*>(e.bias + n0) + jj);
                         float4 o;
-                        o.x = __uint_as_float(v[jj >> 2][(jj & 3) * 4 + 0]) + bv.x;
-                        o.y = __uint_as_float(v[jj >> 2][(jj & 3) * 4 + 1]) + bv.y;
-                        o.z = __uint_as_float(v[jj >> 2][(jj & 3) * 4 + 2]) + bv.z;
-                        o.w = __uint_as_float(v[jj >> 2][(jj & 3) * 4 + 3]) + bv.w;
+                        o.x = acc[c * 32 + jj * 4 + 0] + bv.x;
+                        o.y = acc[c * 32 + jj * 4 + 1] + bv.y;
+                        o.z = acc[c * 32 + jj * 4 + 2] + bv.z;
+                        o.w = acc[c * 32 + jj * 4 + 3] + bv.w;
                         if (e.relu) {
                             o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                         }
@@ -276,43 +335,29 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                         bulk_commit();
                     }
                 }
-            } else {
+            } else if (valid) {
                 // ---- affine-coupling epilogue (layers/coupling.py:73-99) ----
-                float acc[BN];
+                const int half = e.C / 2;
+                const size_t plane = (size_t)g.H * g.W;
+                const size_t base = (size_t)pn * e.C * plane + (size_t)phh * g.W + pw;
+                float rs = 0.f;
 #pragma unroll
-                for (int c = 0; c < BN / 16; ++c) {
-                    uint32_t v[16];
-                    tmem_ld_x16(taddr + c * 16, v);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) acc[c * 16 + i] = __uint_as_float(v[i]);
-                }
-                tc_fence_before();
-                mbar_arrive(&acc_empty[as]);
-                const int pw = t.w0 + row % g.wb, phh = t.h0 + (row / g.wb) % g.hb, pn = t.n0 + row / (g.wb * g.hb);
-                if (pw < g.W && phh < g.H && pn < g.B) {
-                    const int half = e.C / 2;
-                    const size_t plane = (size_t)g.H * g.W;
-                    const size_t base = (size_t)pn * e.C * plane + (size_t)phh * g.W + pw;
-                    float rs = 0.f;
-#pragma unroll
-                    for (int jc = 0; jc < BN / 2; ++jc) {
-                        if (jc < half) {
-                            const float hs = (acc[2 * jc] + __ldg(e.bias + 2 * jc)) * __ldg(e.scale + 2 * jc);
-                            const float tt = (acc[2 * jc + 1] + __ldg(e.bias + 2 * jc + 1)) * __ldg(e.scale + 2 * jc + 1);
-                            const float log_s = 2.0f * tanhf(hs * 0.5f);
-                            const size_t o2 = base + (size_t)(half + jc) * plane;
-                            const float x2 = e.x[o2];
-                            e.y[o2] = e.reverse ? (x2 - tt) * expf(-log_s) : x2 * expf(log_s) + tt;
-                            rs += log_s;
-                            if (e.y != e.x) {
-                                const size_t o1 = base + (size_t)jc * plane;
-                                e.y[o1] = e.x[o1];
-                            }
+                for (int jc = 0; jc < BN / 2; ++jc) {
+                    if (jc < half) {
+                        const float hs = (acc[2 * jc] + __ldg(e.bias + 2 * jc)) * __ldg(e.scale + 2 * jc);
+                        const float tt = (acc[2 * jc + 1] + __ldg(e.bias + 2 * jc + 1)) * __ldg(e.scale + 2 * jc + 1);
+                        const float log_s = 2.0f * tanhf(hs * 0.5f);
+                        const size_t o2 = base + (size_t)(half + jc) * plane;
+                        const float x2 = e.x[o2];
+                        e.y[o2] = e.reverse ? (x2 - tt) * expf(-log_s) : x2 * expf(log_s) + tt;
+                        rs += log_s;
+                        if (e.y != e.x) {
+                            const size_t o1 = base + (size_t)jc * plane;
+                            e.y[o1] = e.x[o1];
                         }
                     }
-                    if (e.rowsum != nullptr) e.rowsum[((size_t)pn * g.H + phh) * g.W + pw] = rs;
                 }
+                if (e.rowsum != nullptr) e.rowsum[((size_t)pn * g.H + phh) * g.W + pw] = rs;
             }
         }
         if (EPI == EPI_NHWC && te == 0) bulk_wait_all();

@@ -10,7 +10,6 @@ int launch_igemm_nhwc_p3(int BN, const CUtensorMap& mapA, const CUtensorMap& map
         case 32: return launch_igemm_t<32, 3, EPI_NHWC>(mapA, mapB, mapOut, g, e, st);
         case 64: return launch_igemm_t<64, 3, EPI_NHWC>(mapA, mapB, mapOut, g, e, st);
         case 128: return launch_igemm_t<128, 3, EPI_NHWC>(mapA, mapB, mapOut, g, e, st);
-        case 256: return launch_igemm_t<256, 3, EPI_NHWC>(mapA, mapB, mapOut, g, e, st);
         default: return FINC_E_UNSUPPORTED;
     }
 }

@@ -174,13 +174,53 @@ class Conv2dZero(nn.Module):
 
 
 class Coupling(FlowLayer):
+    """Affine coupling (layers/coupling.py:44-105).  On CUDA the whole layer -- both 3x3 convolutions,
+    the 1x1, the ReLUs, exp(3 logs), the tanh-bounded scale, the affine map and the per-image
+    log-determinant -- runs on the tensor-core path (finc_coupling_apply_f32: tcgen05 3xTF32
+    implicit GEMMs, hidden activations channels-last, never seen by PyTorch).  Shapes the path does
+    not cover (e.g. width % 32 != 0) and CPU tensors use the PyTorch formulas below.
+
+    `precision`: "fp32" = 3xTF32 split products with fp32 accumulation (matches an fp32 reference
+    to ~1e-6); "tf32" = single-pass TF32 products, PyTorch's default conv precision (~5e-4)."""
+
+    tensor_core = True      # class-wide switch (tests compare both paths)
+    precision = "fp32"
+
     def __init__(self, input_size, width=512):
         super().__init__()
         self.n_channels = input_size[0]
         self.half_channels = self.n_channels // 2
+        self.width = width
         self.net = nn.Sequential(nn.Conv2d(self.half_channels, width, 3, padding=1), nn.ReLU(),
                                  nn.Conv2d(width, width, 1), nn.ReLU(), Conv2dZero(width, self.n_channels))
+        self._blob = None
+        self._blob_key = None
 
+    # ---- tensor-core path -------------------------------------------------------------------------
+    def _params(self):
+        n = self.net
+        return (n[0].weight, n[0].bias, n[2].weight, n[2].bias, n[4].weight, n[4].bias, n[4].logs)
+
+    def _use_tc(self, x):
+        return (self.tensor_core and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+                and _native.coupling_prepared_bytes(self.n_channels, self.width) > 0)
+
+    def prepared(self):
+        """hi / lo split weight blob, rebuilt only when a parameter changed (in-place updates bump
+        `_version`; optimizers and load_state_dict do)"""
+        ps = self._params()
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._blob is None or key != self._blob_key or self._blob.device != ps[0].device:
+            self._blob = _native.coupling_prepare(*[p.detach() for p in ps], self.net[4].logscale_factor,
+                                                  out=self._blob if self._blob is not None
+                                                  and self._blob.device == ps[0].device else None)
+            self._blob_key = key
+        return self._blob
+
+    def _flags(self):
+        return _native.FLAG_TF32_1PASS if self.precision == "tf32" else 0
+
+    # ---- reference formulas (CPU tensors / uncovered shapes / autograd) ----------------------------
     def _st(self, x):
         x1, x2 = x[:, :self.half_channels], x[:, self.half_channels:]
         h = self.net(x1)
@@ -188,10 +228,14 @@ class Coupling(FlowLayer):
         return x1, x2, log_s, h[:, 1::2]
 
     def forward(self, input, context=None):
+        if self._use_tc(input):
+            return _CouplingFn.apply(input, self, *self._params())
         x1, x2, log_s, t = self._st(input)
         return torch.cat([x1, x2 * torch.exp(log_s) + t], dim=1), log_s.flatten(start_dim=1).sum(-1)
 
     def reverse(self, input, context=None):
+        if self._use_tc(input) and not torch.is_grad_enabled():
+            return _native.coupling_apply(input, self.prepared(), self.width, reverse=True, flags=self._flags())[0]
         x1, x2, log_s, t = self._st(input)
         return torch.cat([x1, (x2 - t) * torch.exp(-log_s)], dim=1)
 
@@ -199,8 +243,39 @@ class Coupling(FlowLayer):
         return self.forward(input, context)[1]
 
 
+class _CouplingFn(torch.autograd.Function):
+    """Coupling.forward on the tensor-core kernels; backward recomputes through the PyTorch formulas
+    (the backward kernels are the next step of this row)."""
+
+    @staticmethod
+    def forward(ctx, x, module, *params):
+        ctx.module = module
+        ctx.save_for_backward(x)
+        y, logdet = _native.coupling_apply(x, module.prepared(), module.width, flags=module._flags())
+        return y, logdet
+
+    @staticmethod
+    def backward(ctx, dy, dlogdet):
+        (x,) = ctx.saved_tensors
+        m = ctx.module
+        ps = m._params()
+        with torch.enable_grad():
+            xi = x.detach().requires_grad_(ctx.needs_input_grad[0])
+            x1, x2, log_s, t = m._st(xi)
+            y = torch.cat([x1, x2 * torch.exp(log_s) + t], dim=1)
+            ld = log_s.flatten(start_dim=1).sum(-1)
+            wanted = [xi] if ctx.needs_input_grad[0] else []
+            wanted += [p for p, need in zip(ps, ctx.needs_input_grad[2:]) if need]
+            grads = list(torch.autograd.grad([y, ld], wanted, [dy, dlogdet], allow_unused=True))
+        dx = grads.pop(0) if ctx.needs_input_grad[0] else None
+        dps = [grads.pop(0) if need else None for need in ctx.needs_input_grad[2:]]
+        return (dx, None, *dps)
+
+
 class GaussianPrior(nn.Module):
     """standard normal over `size`; closed form, device follows the input / `device`"""
+
+    is_standard_normal = True  # FlowSequential then fuses log_prob + logdet into finc_gaussian_logp_f32
 
     def __init__(self, size):
         super().__init__()

@@ -127,17 +127,17 @@ class _Slot:
         self.ev_in, self.ev_computed, self.ev_out, self.ev_samp = (torch.cuda.Event() for _ in range(4))
         for lv in stack.levels:
             shp = (B, lv.channels, lv.height, lv.width)
-            self.acts.append([torch.empty(shp, **f) for _ in range(lv.n_units + 1)])
-            self.logdet.append(torch.empty(B, **f))
-            self.logp.append(torch.empty(B, **f))
-            self.dzs.append([torch.empty(shp, **f) for _ in range(lv.n_units + 1)])  # dzs[u] = dL/d acts[u]
-            self.zin.append(torch.empty(shp, **f))
-            self.samp.append([torch.empty(shp, **f) for _ in range(2)])
+            self.acts.append([torch.zeros(shp, **f) for _ in range(lv.n_units + 1)])
+            self.logdet.append(torch.zeros(B, **f))
+            self.logp.append(torch.zeros(B, **f))
+            self.dzs.append([torch.zeros(shp, **f) for _ in range(lv.n_units + 1)])  # dzs[u] = dL/d acts[u]
+            self.zin.append(torch.zeros(shp, **f))
+            self.samp.append([torch.zeros(shp, **f) for _ in range(2)])
             if pinned:
-                self.x_host.append(torch.empty(shp, dtype=torch.float32).pin_memory())
-                self.z_host.append(torch.empty(shp, dtype=torch.float32).pin_memory())
-                self.logp_host.append(torch.empty(B, dtype=torch.float32).pin_memory())
-                self.samp_host.append(torch.empty(shp, dtype=torch.float32).pin_memory())
+                self.x_host.append(torch.zeros(shp, dtype=torch.float32).pin_memory())
+                self.z_host.append(torch.zeros(shp, dtype=torch.float32).pin_memory())
+                self.logp_host.append(torch.zeros(B, dtype=torch.float32).pin_memory())
+                self.samp_host.append(torch.zeros(shp, dtype=torch.float32).pin_memory())
 
 
 class HotPathRunner:
@@ -343,8 +343,24 @@ class HotPathRunner:
 
     # ---- graphs -------------------------------------------------------------------------------
     def prepare(self):
-        """warm up eagerly (binds the device, sets kernel attributes, initialises Adam state),
-        then capture one CUDA graph per (slot, phase).  The all-reduce stays outside graphs."""
+        """warm up eagerly (binds the device, sets kernel attributes), then capture one CUDA graph
+        per (slot, phase).  The all-reduce stays outside graphs.
+
+        Side-effect free for the model: the warm-up passes run every phase -- including the optimizer
+        and, on several ranks, the gradient all-reduce -- on whatever the slot buffers hold (zeros
+        unless the caller filled them), so the parameters and the Adam state (exp_avg, exp_avg_sq,
+        step counter) are snapshotted before and restored after.  Slot buffers (activations,
+        gradients, samples, host buffers) are scratch and ARE overwritten."""
+        saved = [t.detach().clone() for t in (self.stack.flat.data, self.exp_avg, self.exp_avg_sq, self.adam_step)]
+        try:
+            self._prepare_warm_and_capture()
+        finally:
+            for dst, src in zip((self.stack.flat.data, self.exp_avg, self.exp_avg_sq, self.adam_step), saved):
+                dst.copy_(src)
+            self._prepare_weights()
+            torch.cuda.synchronize(self.device)
+
+    def _prepare_warm_and_capture(self):
         self._prepare_weights()
         for s in self.slots:
             if self.host_io:

@@ -82,10 +82,13 @@ def test_host_io_step_and_adam_update():
         s.z_host[li].normal_()
     runner.prepare()
     w1 = stack.flat.detach().clone()
+    # prepare() warms every phase up (optimizer included) but must leave the model untouched
+    assert torch.equal(w1, w0)
+    assert float(runner.adam_step) == 0.0 and not runner.exp_avg.any() and not runner.exp_avg_sq.any()
     runner.step(0)
     torch.cuda.synchronize()
     w2 = stack.flat.detach()
-    assert not torch.equal(w1, w2)
+    assert not torch.equal(w1, w2) and float(runner.adam_step) == 1.0
     # the FInC invariant survives Adam because masked gradients are exactly zero
     for li in range(len(lv)):
         for u in range(lv[li].n_units):

@@ -46,6 +46,13 @@ def test_abi_version_and_error_strings(lib_path):
     assert lib.finc_forward_f32(None, None, None, None, 1, 4, 3, 8, 8, 3, 3, 0xE4, 0, None) == -1
     assert lib.finc_inverse_f32(None, None, None, 1, 17, 3, 8, 8, 3, 3, 0, 0, None) == -1  # G > 16
     assert lib.finc_backward_weight_workspace_bytes(256, 4, 3, 16, 16, 3, 3) >= 4096
+    # tensor-core entry points: sizes are host arithmetic, bad arguments are rejected before any CUDA call
+    assert lib.finc_coupling_prepared_bytes(12, 512) > 4 * (2 * 512 * 64 + 2 * 512 * 512 + 2 * 9 * 16 * 512)
+    assert lib.finc_coupling_prepared_bytes(12, 16) == 0 and lib.finc_coupling_prepared_bytes(13, 512) == 0
+    assert lib.finc_coupling_workspace_bytes(256, 12, 16, 16, 512) >= 4 * 256 * 256 * (64 + 512 + 512)
+    assert lib.finc_coupling_apply_f32(None, None, None, None, None, 0, 1, 12, 8, 8, 512, 0, 0, None) == -1
+    assert lib.finc_tc_conv_nhwc_f32(None, None, None, None, None, 1, 8, 8, 32, 32, 9, 0, 0, None) == -1
+    assert lib.finc_tc_conv_weights_bytes(512, 6, 9, 1) == 2 * 512 * 64 * 4
 
 
 def test_sass_is_sm100a_with_bulk_tma(lib_path):
@@ -60,6 +67,11 @@ def test_sass_is_sm100a_with_bulk_tma(lib_path):
     assert "sm_100a" in out
     assert "UBLKCP" in out  # cp.async.bulk global<->shared
     assert "SYNCS" in out   # mbarrier
+    # tensor-core path: tcgen05.mma / tcgen05.ld / TMA tensor-map loads and stores
+    # (/opt/skills/guides/B200_PROFILING.md "What proves a Blackwell-native kernel")
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UTCBAR"):
+        assert mnemonic in out, mnemonic
+    assert "HMMA.16" not in out and "HGMMA" not in out   # no legacy mma.sync / wgmma paths
 
 
 def test_no_cpu_fallback():

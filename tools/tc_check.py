@@ -50,6 +50,10 @@ def run_case(spec):
         torch.cuda.synchronize()
         ref = F.relu(F.conv2d(x.double(), w.double(), bias.double(), padding=k // 2)).permute(0, 2, 3, 1)
         err = float((y.double() - ref).abs().max() / ref.abs().max())
+        torch.backends.cudnn.allow_tf32 = False
+        y32 = F.relu(F.conv2d(x, w, bias, padding=k // 2)).permute(0, 2, 3, 1)
+        err32 = float((y32.double() - ref).abs().max() / ref.abs().max())
+        print(f"   (cuDNN fp32 vs fp64: {err32:.3e}; ours vs cuDNN fp32: {float((y - y32).abs().max() / ref.abs().max()):.3e})")
         bad = int(((y.double() - ref).abs() > 1e-2 * ref.abs().max()).sum())
         print(f"{spec}: max-norm rel err {err:.3e}, elements off by >1%: {bad} of {ref.numel()}")
         if bad:
@@ -85,6 +89,11 @@ def run_case(spec):
         ey = float((y.double() - yr).abs().max() / yr.abs().max())
         el = float((ld.double() - ldr).abs().max() / ldr.abs().max().clamp_min(1e-30))
         rt = float((xr - x).abs().max())
+        with torch.no_grad():
+            y32, ld32 = cp(x)
+        print(f"   (PyTorch fp32 vs fp64: y {float((y32.double() - yr).abs().max() / yr.abs().max()):.3e}, "
+              f"logdet {float((ld32.double() - ldr).abs().max() / ldr.abs().max()):.3e}; ours vs PyTorch fp32: "
+              f"y {float((y - y32).abs().max() / yr.abs().max()):.3e}, logdet {float((ld - ld32).abs().max() / ldr.abs().max()):.3e})")
         print(f"{spec}: y rel {ey:.3e}, logdet rel {el:.3e}, round trip max-abs {rt:.3e}")
         tol = 2e-3 if npass == 1 else 1e-5
         return ey < tol and el < tol and rt < (1e-2 if npass == 1 else 1e-4)

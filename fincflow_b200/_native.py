@@ -39,7 +39,7 @@ SYMBOLS = (
     "finc_gaussian_logp_f32", "finc_debug_timestamps", "finc_prepared_weights_bytes", "finc_prepare_weights_f32",
     "finc_squeeze_f32", "finc_unsqueeze_f32", "finc_adam_step_f32", "finc_allreduce_adam_f32", "finc_affine1x1_f32",
     "finc_affine1x1_backward_weight_workspace_bytes", "finc_affine1x1_backward_weight_f32",
-    "finc_tc_conv_weights_bytes", "finc_tc_conv_prepare_weights_f32", "finc_tc_conv_nhwc_f32",
+    "finc_preprocess_f32", "finc_tc_conv_weights_bytes", "finc_tc_conv_prepare_weights_f32", "finc_tc_conv_nhwc_f32",
     "finc_coupling_prepared_bytes", "finc_coupling_workspace_bytes", "finc_coupling_prepare_f32",
     "finc_coupling_apply_f32",
 )
@@ -97,6 +97,8 @@ def load():
     lib.finc_prepared_weights_bytes.argtypes = [i] + dims
     lib.finc_prepare_weights_f32.restype = i
     lib.finc_prepare_weights_f32.argtypes = [p, p, i, i, sz, sz, *dims, u, p]
+    lib.finc_preprocess_f32.restype = i
+    lib.finc_preprocess_f32.argtypes = [p, p, p, p, i, ctypes.c_long, ctypes.c_float, i, p]
     lib.finc_tc_conv_weights_bytes.restype = sz
     lib.finc_tc_conv_weights_bytes.argtypes = [i, i, i, i]
     lib.finc_tc_conv_prepare_weights_f32.restype = i
@@ -387,6 +389,23 @@ def affine1x1_backward_weight(dy, x, want_bias=True):
                                                      0 if db is None else db.data_ptr(), ws.data_ptr(), ws.numel(),
                                                      B, C, HW, _stream(x)), "finc_affine1x1_backward_weight_f32", 2)
     return dA, db
+
+
+def preprocess(x, noise=None, alpha=1e-6, reverse=False, want_logdet=True):
+    """dequantise + normalise + logit (and their log-determinants) in one kernel; reverse = sigmoid ... floor
+    (fastflow_cifar_multi_gpu.py:162-186)"""
+    x = _prep(x, "x")
+    _bind_device(x)
+    B = int(x.shape[0])
+    D = x.numel() // max(B, 1)
+    y = torch.empty_like(x)
+    logdet = torch.empty(B, dtype=torch.float32, device=x.device) if (want_logdet and not reverse) else None
+    if noise is not None:
+        noise = _prep(noise, "noise")
+    _check(load().finc_preprocess_f32(x.data_ptr(), None if noise is None else noise.data_ptr(), y.data_ptr(),
+                                      None if logdet is None else logdet.data_ptr(), B, D, float(alpha), int(reverse),
+                                      _stream(x)), "finc_preprocess_f32")
+    return y, logdet
 
 
 # ---------------------------------------------------------------------------------------------

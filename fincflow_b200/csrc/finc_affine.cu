@@ -339,3 +339,50 @@ int launch_affine1x1(const float* x, const float* A, const float* bias, float* y
 }
 
 }  // namespace finc
+
+// ---------------------------------------------------------------------------------------------
+// Preprocess (fastflow_cifar_multi_gpu.py:162-186): Dequantization (layers/dequantize.py:13-19),
+// Normalization(0, 256), Normalization(-alpha, 1 / (1 - 2 alpha)) (layers/normalize.py:18-31) and
+// LogitTransform (layers/transforms.py:11-18) with their four log-determinants, as ONE pass:
+//   p = ((x + u) / 256 + alpha) * (1 - 2 alpha);   y = log p - log(1 - p)
+//   logdet[n] = D * (log(1 - 2 alpha) - log 256) + sum_d (-log p - log(1 - p))
+// reverse: x = floor((sigmoid(y) / (1 - 2 alpha) - alpha) * 256).  One CTA per image, fixed-order sum.
+// ---------------------------------------------------------------------------------------------
+namespace finc {
+
+__global__ void preprocess_kernel(const float* __restrict__ x, const float* __restrict__ u, float* __restrict__ y,
+                                  float* __restrict__ logdet, long D, float alpha, int reverse) {
+    __shared__ float red[256];
+    const long base = (long)blockIdx.x * D;
+    const float s = 1.f - 2.f * alpha;
+    float acc = 0.f;
+    for (long d = threadIdx.x; d < D; d += blockDim.x) {
+        if (reverse) {
+            const float p = 1.f / (1.f + expf(-x[base + d]));
+            y[base + d] = floorf((p / s - alpha) * 256.f);
+        } else {
+            const float v = x[base + d] + (u != nullptr ? u[base + d] : 0.f);
+            const float p = (v / 256.f + alpha) * s;
+            const float lp = logf(p), lq = logf(1.f - p);
+            y[base + d] = lp - lq;
+            acc += -lp - lq;
+        }
+    }
+    if (reverse || logdet == nullptr) return;
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) logdet[blockIdx.x] = red[0] + (float)D * (logf(s) - logf(256.f));
+}
+
+int launch_preprocess(const float* x, const float* u, float* y, float* logdet, int B, long D, float alpha, int reverse,
+                      cudaStream_t st) {
+    if (B == 0) return 0;
+    preprocess_kernel<<<B, 256, 0, st>>>(x, u, y, logdet, D, alpha, reverse);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace finc

@@ -243,6 +243,14 @@ int finc_affine1x1_f32(const float* x, const float* A, const float* bias, float*
     return launch_affine1x1(x, A, bias, y, B, C, HW, (cudaStream_t)stream);
 }
 
+int finc_preprocess_f32(const float* x, const float* noise, float* y, float* logdet, int B, long D, float alpha,
+                        int reverse, void* stream) {
+    if (B < 0 || D < 1 || !(alpha >= 0.f && alpha < 0.5f)) return FINC_E_BADARG;
+    if (B == 0) return FINC_OK;
+    if (!x || !y) return FINC_E_BADARG;
+    return launch_preprocess(x, noise, y, logdet, B, D, alpha, reverse, (cudaStream_t)stream);
+}
+
 size_t finc_affine1x1_backward_weight_workspace_bytes(int B, int C, long HW) {
     if (B < 0 || C < 1 || C > 4096 || HW < 1) return 0;
     return affine1x1_wgrad_workspace_floats(B, C, HW) * sizeof(float);

@@ -9,23 +9,44 @@
 
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
+
 namespace finc {
 namespace tc {
 
-int launch_igemm_nhwc_p1(int BN, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const Geom&, const EpiArgs&,
-                         cudaStream_t);
-int launch_igemm_nhwc_p3(int BN, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const Geom&, const EpiArgs&,
-                         cudaStream_t);
-int launch_igemm_coupling_p1(int BN, const CUtensorMap&, const CUtensorMap&, const Geom&, const EpiArgs&, cudaStream_t);
-int launch_igemm_coupling_p3(int BN, const CUtensorMap&, const CUtensorMap&, const Geom&, const EpiArgs&, cudaStream_t);
+#define FINC_TC_DECL(P, CL)                                                                                      \
+    int launch_igemm_nhwc_p##P##_c##CL(int BN, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const Geom&, \
+                                       const EpiArgs&, cudaStream_t);
+FINC_TC_DECL(1, 1) FINC_TC_DECL(1, 2) FINC_TC_DECL(1, 4) FINC_TC_DECL(3, 1) FINC_TC_DECL(3, 2) FINC_TC_DECL(3, 4)
+#undef FINC_TC_DECL
+int launch_igemm_rows_p1(int BN, const CUtensorMap&, const CUtensorMap&, const Geom&, const EpiArgs&, cudaStream_t);
+int launch_igemm_rows_p3(int BN, const CUtensorMap&, const CUtensorMap&, const Geom&, const EpiArgs&, cudaStream_t);
 
-int launch_igemm_nhwc(int BN, int npass, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const Geom& g,
-                      const EpiArgs& e, cudaStream_t st) {
-    return npass == 1 ? launch_igemm_nhwc_p1(BN, a, b, o, g, e, st) : launch_igemm_nhwc_p3(BN, a, b, o, g, e, st);
+int launch_igemm_nhwc(int BN, int npass, int cluster, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o,
+                      const Geom& g, const EpiArgs& e, cudaStream_t st) {
+    if (npass == 1)
+        return cluster == 4   ? launch_igemm_nhwc_p1_c4(BN, a, b, o, g, e, st)
+               : cluster == 2 ? launch_igemm_nhwc_p1_c2(BN, a, b, o, g, e, st)
+                              : launch_igemm_nhwc_p1_c1(BN, a, b, o, g, e, st);
+    return cluster == 4   ? launch_igemm_nhwc_p3_c4(BN, a, b, o, g, e, st)
+           : cluster == 2 ? launch_igemm_nhwc_p3_c2(BN, a, b, o, g, e, st)
+                          : launch_igemm_nhwc_p3_c1(BN, a, b, o, g, e, st);
 }
-int launch_igemm_coupling(int BN, int npass, const CUtensorMap& a, const CUtensorMap& b, const Geom& g, const EpiArgs& e,
-                          cudaStream_t st) {
-    return npass == 1 ? launch_igemm_coupling_p1(BN, a, b, g, e, st) : launch_igemm_coupling_p3(BN, a, b, g, e, st);
+int launch_igemm_rows(int BN, int npass, const CUtensorMap& a, const CUtensorMap& b, const Geom& g, const EpiArgs& e,
+                      cudaStream_t st) {
+    return npass == 1 ? launch_igemm_rows_p1(BN, a, b, g, e, st) : launch_igemm_rows_p3(BN, a, b, g, e, st);
+}
+
+// CTAs per cluster for the channels-last GEMMs: FINC_TC_CLUSTER = 1 | 2 | 4 (experiments); default below
+static int cluster_size(int BN, int m_tiles) {
+    static int env = -1;
+    if (env < 0) {
+        const char* v = getenv("FINC_TC_CLUSTER");
+        env = v ? atoi(v) : 0;
+    }
+    int cl = env > 0 ? env : 1;   // measured on B200: 1 and 2 tie (the layer is not L2-bound), 4 loses to the lock-step
+    while (cl > 1 && ((BN / cl) % 8 != 0 || BN % cl != 0 || m_tiles < cl || (BN == 32 && cl == 4))) cl >>= 1;
+    return cl;
 }
 
 // ---- tensor maps ------------------------------------------------------------------------------
@@ -161,6 +182,56 @@ __global__ void rowsum_reduce_kernel(const float* __restrict__ rowsum, float* __
     if (threadIdx.x == 0) logdet[n] = (accumulate ? logdet[n] : 0.f) + red[0];
 }
 
+// Last step of the coupling layer.  The 3x3 convolution width -> C ran as ONE plain GEMM
+//   Y[pixel, tap * N3pad + n] = sum_c h2[pixel, c] * W3[n, c, tap]
+// (the activation tile is read once, not nine times, and the MMAs are 9x wider than N = C); here
+// every pixel gathers its nine neighbours' tap columns, h[n] = sum_tap Y[pixel + offset(tap), tap, n],
+// and applies the coupling (layers/coupling.py:73-99): h = (h + bias) * exp(3 logs),
+// log_s = 2 tanh(h[2j] / 2), t = h[2j+1], y2 = x2 * exp(log_s) + t  (reverse: (x2 - t) * exp(-log_s)).
+__global__ void coupling_gather_kernel(const float* __restrict__ Y, const float* __restrict__ bias,
+                                       const float* __restrict__ scale, const float* x, float* y,
+                                       float* __restrict__ rowsum, int B, int C, int H, int W, int N3pad, int reverse) {
+    const long np = (long)B * H * W;
+    const long pix = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (pix >= np) return;
+    const int pw = (int)(pix % W), ph = (int)((pix / W) % H);
+    const long n = pix / ((long)W * H);
+    const int half = C / 2, ldy = 9 * N3pad;
+    const size_t plane = (size_t)H * W;
+    const size_t base = (size_t)n * C * plane + (size_t)ph * W + pw;
+    const float* rows[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const int hh = ph + tap / 3 - 1, ww = pw + tap % 3 - 1;
+        rows[tap] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? Y + (pix + (long)(tap / 3 - 1) * W + (tap % 3 - 1)) * ldy + tap * N3pad
+                                                             : nullptr;
+    }
+    float rs = 0.f;
+    for (int jc = 0; jc < half; ++jc) {
+        float hs = 0.f, tt = 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            if (rows[tap] != nullptr) {
+                const float2 v = __ldg(reinterpret_cast<const float2*>(rows[tap]) + jc);
+                hs += v.x;
+                tt += v.y;
+            }
+        }
+        hs = (hs + __ldg(bias + 2 * jc)) * __ldg(scale + 2 * jc);
+        tt = (tt + __ldg(bias + 2 * jc + 1)) * __ldg(scale + 2 * jc + 1);
+        const float log_s = 2.0f * tanhf(hs * 0.5f);
+        const size_t o2 = base + (size_t)(half + jc) * plane;
+        const float x2 = x[o2];
+        y[o2] = reverse ? (x2 - tt) * expf(-log_s) : x2 * expf(log_s) + tt;
+        rs += log_s;
+        if (y != x) {
+            const size_t o1 = base + (size_t)jc * plane;
+            y[o1] = x[o1];
+        }
+    }
+    if (rowsum != nullptr) rowsum[pix] = rs;
+}
+
 // bias / scale vectors of the zero-initialised last conv: scale = exp(logscale_factor * logs)
 __global__ void coupling_vectors_kernel(const float* __restrict__ b1, const float* __restrict__ b2,
                                         const float* __restrict__ b3, const float* __restrict__ logs3, float factor,
@@ -205,7 +276,7 @@ static bool coupling_supported(int C, int width) {
 }
 
 struct Workspace {
-    size_t a1, h1, h2, rowsum, total;  // float offsets
+    size_t a1, h1, h2, y3, rowsum, total;  // float offsets
 };
 static Workspace coupling_workspace(int B, int C, int H, int W, int width) {
     const CouplingLayout L = coupling_layout(C, width);
@@ -215,6 +286,7 @@ static Workspace coupling_workspace(int B, int C, int H, int W, int width) {
     w.a1 = o; o += np * L.K1pad;
     w.h1 = o; o += np * width;
     w.h2 = o; o += np * width;
+    w.y3 = o; o += np * 9 * L.N3pad;
     w.rowsum = o; o += (np + 31) / 32 * 32;
     w.total = o;
     return w;
@@ -231,10 +303,11 @@ static int conv_nhwc(const float* x, const float* wsplit, const float* bias, con
                      int W, int Cpad, int Npad, int taps, int relu, int npass, cudaStream_t st) {
     const int BN = pick_bn_nhwc(Npad);
     const Geom g = make_geom(B, H, W, taps, Cpad, Npad, BN);
+    const int cl = cluster_size(BN, g.tiles_w * g.tiles_h * g.tiles_n);
     CUtensorMap mA, mB, mO;
     int rc = map_nhwc(&mA, x, Cpad, W, H, B, g.wb, g.hb, g.nb);
     if (rc) return rc;
-    rc = map_weights(&mB, wsplit, (long)2 * taps * Npad, Cpad, BN);
+    rc = map_weights(&mB, wsplit, (long)2 * taps * Npad, Cpad, BN / cl);
     if (rc) return rc;
     rc = map_nhwc(&mO, y, Npad, W, H, B, g.wb, g.hb, g.nb);
     if (rc) return rc;
@@ -242,7 +315,7 @@ static int conv_nhwc(const float* x, const float* wsplit, const float* bias, con
     e.bias = bias;
     e.relu = relu;
     e.mask = mask;
-    return launch_igemm_nhwc(BN, npass, mA, mB, mO, g, e, st);
+    return launch_igemm_nhwc(BN, npass, cl, mA, mB, mO, g, e, st);
 }
 
 }  // namespace tc
@@ -330,23 +403,27 @@ int finc_coupling_apply_f32(const float* x, float* y, float* logdet, const void*
     rc = conv_nhwc(wsp + ws.h1, p + L.w2, p + L.b2, nullptr, wsp + ws.h2, B, H, W, width, width, 1, 1, npass, st);
     if (rc) return rc;
 
-    const Geom g = make_geom(B, H, W, 9, width, L.N3pad, L.N3pad);
+    // third convolution as one GEMM over all nine taps (weight rows [tap][n] are already contiguous) ...
+    const int n3 = 9 * L.N3pad;   // a multiple of 144
+    const int BN = 144;
+    const Geom g = make_geom(B, H, W, 1, width, n3, BN);
     CUtensorMap mA, mB;
     rc = map_nhwc(&mA, wsp + ws.h2, width, W, H, B, g.wb, g.hb, g.nb);
     if (rc) return rc;
-    rc = map_weights(&mB, p + L.w3, (long)2 * 9 * L.N3pad, width, L.N3pad);
+    rc = map_weights(&mB, p + L.w3, (long)2 * n3, width, BN);
     if (rc) return rc;
     EpiArgs e{};
-    e.bias = p + L.b3;
-    e.scale = p + L.s3;
-    e.x = x;
-    e.y = y;
-    e.rowsum = (logdet != nullptr && !reverse) ? wsp + ws.rowsum : nullptr;
-    e.C = C;
-    e.reverse = reverse;
-    rc = launch_igemm_coupling(L.N3pad, npass, mA, mB, g, e, st);
+    e.y = wsp + ws.y3;
+    e.ld_out = n3;
+    rc = launch_igemm_rows(BN, npass, mA, mB, g, e, st);
     if (rc) return rc;
-    if (e.rowsum != nullptr) {
+    // ... then the nine-neighbour gather + coupling math
+    float* rowsum = (logdet != nullptr && !reverse) ? wsp + ws.rowsum : nullptr;
+    coupling_gather_kernel<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(wsp + ws.y3, p + L.b3, p + L.s3, x, y, rowsum, B,
+                                                                        C, H, W, L.N3pad, reverse);
+    rc = (int)cudaGetLastError();
+    if (rc) return rc;
+    if (rowsum != nullptr) {
         rowsum_reduce_kernel<<<B, 128, 0, st>>>(wsp + ws.rowsum, logdet, H * W,
                                                (flags & FINC_FLAG_LOGDET_ACCUMULATE) ? 1 : 0);
         rc = (int)cudaGetLastError();

@@ -7,17 +7,17 @@ namespace finc {
 namespace tc {
 
 // launchers implemented by the template-instantiation units; return cudaError_t as int, or
-// FINC_E_UNSUPPORTED when (BN, npass) is not instantiated
-int launch_igemm_nhwc(int BN, int npass, const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapOut,
-                      const Geom& g, const EpiArgs& e, cudaStream_t st);
-int launch_igemm_coupling(int BN, int npass, const CUtensorMap& mapA, const CUtensorMap& mapB, const Geom& g,
-                          const EpiArgs& e, cudaStream_t st);
+// FINC_E_UNSUPPORTED when the variant is not instantiated.  `cluster` = CTAs sharing one weight tile.
+int launch_igemm_nhwc(int BN, int npass, int cluster, const CUtensorMap& mapA, const CUtensorMap& mapB,
+                      const CUtensorMap& mapOut, const Geom& g, const EpiArgs& e, cudaStream_t st);
+int launch_igemm_rows(int BN, int npass, const CUtensorMap& mapA, const CUtensorMap& mapB, const Geom& g,
+                      const EpiArgs& e, cudaStream_t st);
 
-template <int BN, int NPASS, int EPI>
+template <int BN, int NPASS, int EPI, int CL, int EW>
 inline int launch_igemm_t(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapOut, const Geom& g,
                           const EpiArgs& e, cudaStream_t st) {
-    using C = Cfg<BN, NPASS>;
-    auto kern = igemm_kernel<BN, NPASS, EPI>;
+    using C = Cfg<BN, NPASS, EW>;
+    auto kern = igemm_kernel<BN, NPASS, EPI, CL, EW>;
     constexpr int smem = C::kSmemBytes + 1024;  // + slack for the manual 1024-byte alignment
     static_assert(smem <= kSmemLimit, "shared memory budget");
     static bool configured[64] = {};
@@ -28,19 +28,32 @@ inline int launch_igemm_t(const CUtensorMap& mapA, const CUtensorMap& mapB, cons
         if (err != cudaSuccess) return (int)err;
         configured[dev] = true;
     }
-    const int tiles = g.tiles_w * g.tiles_h * g.tiles_n * g.n_tiles;
-    const int grid = tiles < sm_count_cached() ? tiles : sm_count_cached();
-    if (grid <= 0) return 0;
+    const int m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
+    const int cluster_tiles = (m_tiles + CL - 1) / CL * g.n_tiles;
+    const int max_clusters = sm_count_cached() / CL;
+    const int clusters = cluster_tiles < max_clusters ? cluster_tiles : max_clusters;
+    if (clusters <= 0) return 0;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid, 1, 1);
-    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.gridDim = dim3((unsigned)(clusters * CL), 1, 1);
+    cfg.blockDim = dim3(C::kThreads, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (CL > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = CL;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = na;
     return (int)cudaLaunchKernelEx(&cfg, kern, mapA, mapB, mapOut, g, e);
 }
 

@@ -1,0 +1,17 @@
+// explicit instantiations: channels-last epilogue, 1-pass TF32, clusters of 4
+#include "tc_host.cuh"
+
+namespace finc {
+namespace tc {
+
+int launch_igemm_nhwc_p1_c4(int BN, const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapOut,
+                              const Geom& g, const EpiArgs& e, cudaStream_t st) {
+    switch (BN) {
+        case 64: return launch_igemm_t<64, 1, EPI_NHWC, 4, 4>(mapA, mapB, mapOut, g, e, st);
+        case 128: return launch_igemm_t<128, 1, EPI_NHWC, 4, 8>(mapA, mapB, mapOut, g, e, st);
+        default: return FINC_E_UNSUPPORTED;
+    }
+}
+
+}  // namespace tc
+}  // namespace finc

@@ -322,13 +322,24 @@ class SplitPrior(FlowLayer):
 # flow
 # ---------------------------------------------------------------------------------------------
 class Preprocess(nn.Module):
+    """Dequantization, Normalization(0, 256), Normalization(-alpha, 1/(1-2 alpha)), LogitTransform
+    (fastflow_cifar_multi_gpu.py:162-186).  On CUDA the four layers and their log-determinants are ONE
+    kernel (finc_preprocess_f32); the sub-modules stay for the reference's state-dict keys
+    (`preprocess.layers.1.translation`, ...) and for CPU tensors."""
+
+    fused = True
+
     def __init__(self, size):
         super().__init__()
-        alpha = 1e-6
+        self.alpha = alpha = 1e-6
         self.layers = nn.Sequential(Dequantization(), Normalization(0, 256),
                                     Normalization(-alpha, 1 / (1 - 2 * alpha)), LogitTransform())
 
     def forward(self, x):
+        if self.fused and x.is_cuda and x.dtype == torch.float32 and not x.requires_grad:
+            deq = self.layers[0]
+            u = deq.fixed_noise.to(x.device) if deq.fixed_noise is not None else torch.rand_like(x)
+            return _native.preprocess(x, u, self.alpha)
         logdet = 0
         for layer in self.layers:
             x, ld = layer(x)
@@ -336,6 +347,8 @@ class Preprocess(nn.Module):
         return x, logdet
 
     def reverse(self, x):
+        if self.fused and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled():
+            return _native.preprocess(x, None, self.alpha, reverse=True)[0]
         for layer in reversed(self.layers):
             x = layer.reverse(x)
         return x

@@ -165,6 +165,16 @@ int finc_allreduce_adam_f32(const void* peer_grad, const void* peer_signal, void
 int finc_squeeze_f32(const float* x, float* y, int B, int C, int H, int W, void* stream);
 int finc_unsqueeze_f32(const float* x, float* y, int B, int C4, int H, int W, void* stream);
 
+/* Input preprocessing of the image flows, forward and reverse, in one pass (x, y: [B, D] contiguous):
+ *   forward: p = ((x + noise) / 256 + alpha) * (1 - 2 alpha);  y = log p - log(1 - p)
+ *            logdet[n] = D * (log(1 - 2 alpha) - log 256) + sum_d (-log p - log(1 - p))   (logdet may be NULL)
+ *   reverse: y = floor((sigmoid(x) / (1 - 2 alpha) - alpha) * 256)
+ * `noise` = the dequantisation noise u ~ U[0,1) drawn by the caller (NULL = 0).  Replaces the four
+ * layers of Preprocess (fastflow_cifar_multi_gpu.py:162-186: layers/dequantize.py:13-19,
+ * layers/normalize.py:18-31 twice, layers/transforms.py:11-18) and their logdet adds. */
+int finc_preprocess_f32(const float* x, const float* noise, float* y, float* logdet, int B, long D, float alpha,
+                        int reverse, void* stream);
+
 /* Per-pixel affine map over the channel axis, x and y [B, C, HW] contiguous (NCHW with HW = H*W):
  *   y[n, o, p] = sum_i A[o, i] * x[n, i, p] + (bias ? bias[o] : 0)           A: [C, C] row-major
  * One pass for the glue that follows every FastFlowUnit in the reference's flow step

@@ -185,3 +185,26 @@ def test_affine1x1_backward_weight(shape):
     assert torch.equal(dA, dA2) and torch.equal(db, db2)
     dA3, none = _native.affine1x1_backward_weight(dy.cuda(), x.cuda(), want_bias=False)
     assert none is None and torch.equal(dA, dA3)
+
+
+def test_fused_preprocess_matches_the_four_layers():
+    """finc_preprocess_f32 == Dequantization -> Normalization(0,256) -> Normalization(-a, 1/(1-2a)) -> Logit
+    with the summed log-determinants (fastflow_cifar_multi_gpu.py:162-186), and its reverse"""
+    from fincflow_b200.flows import Preprocess
+
+    torch.manual_seed(4)
+    pre = Preprocess((3, 32, 32)).cuda()
+    x = torch.randint(0, 256, (37, 3, 32, 32), device="cuda").float()
+    pre.layers[0].fixed_noise = torch.rand_like(x)
+    y, ld = pre(x)
+    Preprocess.fused = False
+    try:
+        y_ref, ld_ref = pre(x)
+        x_back_ref = pre.reverse(y_ref)
+    finally:
+        Preprocess.fused = True
+    assert rel_err(y.cpu().numpy(), y_ref.cpu().numpy()) <= 1e-6
+    assert rel_err(ld.cpu().numpy(), ld_ref.cpu().numpy()) <= 1e-6
+    with torch.no_grad():
+        x_back = pre.reverse(y)
+    assert torch.equal(x_back, x) and torch.equal(x_back_ref, x)

@@ -48,6 +48,132 @@ def levels():
     return cifar10_levels(UNITS_PER_LEVEL, KSIZE)
 
 
+def extra_workload_specs(world):
+    """the other configurations the metric names (BASELINE.json configs[0,1,3,4] + configs[2] with the
+    GLOBAL batch fixed): name -> (levels, per-GPU batch, scaling, phases to run)"""
+    from fincflow_b200.stack import LevelSpec, cifar10_levels, imagenet32_levels, imagenet64_levels, mnist_levels
+
+    allp = ("forward_logdet", "backward", "optimizer", "inverse")
+    return {
+        "cfg1_single_layer": dict(levels=[LevelSpec(4, 14, 14, 1, (3, 3))], batch=64, scaling="weak", phases=allp,
+                                  what="one FastFlowUnit(4) on the squeezed 1x28x28 MNIST shape, batch 64 per GPU"),
+        "cfg2_mnist": dict(levels=mnist_levels(), batch=128, scaling="weak", phases=allp,
+                           what="MNIST flow skeleton: 16 units [4,14,14] + 1 unit [8,7,7], batch 128 per GPU"),
+        "cfg3_strong": dict(levels=cifar10_levels(UNITS_PER_LEVEL, KSIZE), batch=max(PER_GPU_BATCH // world, 1),
+                            scaling="strong", phases=allp,
+                            what="the headline workload with the GLOBAL batch fixed at 256 (256 / N per GPU)"),
+        "cfg4_imagenet32": dict(levels=imagenet32_levels(), batch=512, scaling="weak", phases=allp,
+                                what="ImageNet32 flow skeleton: 3 levels x 48 units, batch 512 per GPU"),
+        "cfg5_imagenet64_k3": dict(levels=imagenet64_levels(48, 3), batch=max(1024 // world, 1), scaling="strong",
+                                   phases=("inverse",),
+                                   what="ImageNet64 flow skeleton k=3 (48,48,48,1 units), SAMPLING only, 1024 images sharded by batch"),
+        "cfg5_imagenet64_k5": dict(levels=imagenet64_levels(48, 5), batch=max(1024 // world, 1), scaling="strong",
+                                   phases=("inverse",),
+                                   what="ImageNet64 flow skeleton k=5, SAMPLING only, 1024 images sharded by batch"),
+    }
+
+
+def run_extra_workloads(torch, dev, world, rank, pg, K, names=None):
+    """phase times of the other named configurations through the same HotPathRunner (CUDA graphs, one
+    slot); multi-GPU: every rank runs its shard, times are the max over ranks"""
+    from fincflow_b200.stack import FincStack, HotPathRunner
+
+    out = []
+    K = max(3, min(K, 20))
+    for name, spec in extra_workload_specs(world).items():
+        if names is not None and name not in names:
+            continue
+        try:
+            torch.manual_seed(0)
+            stack = FincStack(spec["levels"]).to(dev)
+            B = spec["batch"]
+            runner = HotPathRunner(stack, B, dev, slots=1, process_group=pg if "optimizer" in spec["phases"] else None)
+            g = torch.Generator(device=dev).manual_seed(4000 + rank)
+            for li in range(len(spec["levels"])):
+                runner.slots[0].acts[li][0].normal_(generator=g)
+                runner.slots[0].zin[li].normal_(generator=g)
+            runner.prepare()
+            idx = [HotPathRunner.PHASES.index(p) for p in spec["phases"]]
+            for _ in range(3):
+                for p in idx:
+                    runner.run_phase(0, p)
+            if world > 1:
+                torch.distributed.barrier()
+            torch.cuda.synchronize(dev)
+            evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(idx) + 1)] for _ in range(K)]
+            for i in range(K):
+                for j, p in enumerate(idx):
+                    evs[i][j].record()
+                    runner.run_phase(0, p)
+                evs[i][len(idx)].record()
+            torch.cuda.synchronize(dev)
+            tot = evs[0][0].elapsed_time(evs[K - 1][len(idx)]) / K
+            ph = [sum(evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(K)) / K for j in range(len(idx))]
+            t = torch.tensor([tot] + ph, device=dev, dtype=torch.float64)
+            if world > 1:
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            tot, ph = float(t[0]), [float(v) for v in t[1:]]
+            pm = dict(zip(spec["phases"], ph))
+            gb = B * world
+            elems = sum(lv.n_units * B * lv.dim for lv in spec["levels"])
+            ips = {}
+            if "forward_logdet" in pm:
+                ips["forward_logdet"] = round(gb / (pm["forward_logdet"] * 1e-3))
+                ips["train_step"] = round(gb / ((pm["forward_logdet"] + pm["backward"] + pm["optimizer"]) * 1e-3))
+            if "inverse" in pm:
+                ips["inverse_sampling"] = round(gb / (pm["inverse"] * 1e-3))
+            peak, _ = measured_peak()
+            out.append({"name": name, "what": spec["what"], "per_gpu_batch": B, "global_batch": gb,
+                        "scaling": spec["scaling"], "steps": K, "ms_per_step": round(tot, 4),
+                        "phases_ms": {k: round(v, 4) for k, v in pm.items()}, "images_per_s": ips,
+                        "frac_of_hbm_peak": {k: round(8 * elems * (1.5 if k == "backward" else 1.0) / (v * 1e-3) / 1e9 / peak, 4)
+                                             for k, v in pm.items() if k != "optimizer"}})
+            del runner, stack
+            torch.cuda.empty_cache()
+        except Exception as e:  # never fail the bench line over an extra workload
+            out.append({"name": name, "error": repr(e)})
+    return out
+
+
+def gpu_reference_detail(torch, dev, ours_phase_ms):
+    """the REFERENCE's own GPU path on the same box, same step: F.pad + conv2d fwd / autograd bwd with TF32
+    off + `grad * mask` + Adam, and FastFlowUnit.reverse_level2 on the reference's CUDA extension (compiled
+    unmodified into oracle/_ref by oracle/build_ref_cuda.py)"""
+    try:
+        from oracle.reference_path import ReferenceGpuStack
+
+        old = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        ref = ReferenceGpuStack(levels(), PER_GPU_BATCH, dev)
+
+        def timed(fn, n):
+            fn()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            e1.synchronize()
+            return e0.elapsed_time(e1) / n
+
+        fwd = timed(ref.forward_only, 5)
+        train = timed(ref.train_step, 5)
+        samp = timed(ref.sample, 2)
+        torch.backends.cudnn.allow_tf32 = old
+        ours_train = ours_phase_ms["forward_logdet"] + ours_phase_ms["backward"] + ours_phase_ms["optimizer"]
+        B = PER_GPU_BATCH
+        return {"what": "reference GPU path (PyTorch/cuDNN fp32 with TF32 off + its cinc_cuda_level2 extension), same workload, 1 GPU",
+                "forward_ms": round(fwd, 3), "train_step_ms": round(train, 3), "sample_ms": round(samp, 3),
+                "images_per_s": {"forward_logdet": round(B / fwd * 1e3), "train_step": round(B / train * 1e3),
+                                 "inverse_sampling": round(B / samp * 1e3)},
+                "speedup_ours": {"forward_logdet": round(fwd / ours_phase_ms["forward_logdet"], 1),
+                                 "train_step": round(train / ours_train, 1),
+                                 "inverse_sampling": round(samp / ours_phase_ms["inverse"], 1)}}
+    except Exception as e:
+        return {"error": repr(e)}
+
+
 def measured_peak():
     try:
         with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
@@ -138,18 +264,28 @@ def run_reference_cpu(steps, warmup, max_seconds=None):
     }
 
 
+def base_config(world):
+    """the keys both arms print identically (the driver compares `config` between the arms)"""
+    return {"workload": WORKLOAD, "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * world,
+            "units_per_level": UNITS_PER_LEVEL, "kernel_size": KSIZE}
+
+
+def reference_config(world):
+    return base_config(world)
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     # a step of the reference's CPU path takes ~0.6 s on the pool's hosts: bound the whole run to a few minutes
-    r = run_reference_cpu(args.steps, min(args.warmup, 3), max_seconds=180.0)
+    r = run_reference_cpu(args.steps, max(args.warmup, 3), max_seconds=180.0)
     line = {
         "impl": "reference", "metric": "images/sec fwd+logdet, train step, and inverse sampling", "value": r["value"],
-        "unit": "images/s", "n_gpus": args.gpus, "steps": r["steps"], "steps_requested": args.steps, "warmup": min(args.warmup, 3),
+        "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "steps_measured": r["steps"], "warmup": max(args.warmup, 3),
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_gpu_batch": PER_GPU_BATCH, "device": "host CPU"},
+        "config": reference_config(args.gpus),
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -431,23 +567,38 @@ def main_ours(args):
                                                          # drawn on the device, like the reference's model.sample)
     d2h = act_bytes + sum(4 * B for _ in lvls)           # samples + logp
     launches = e2e_runner.launches_per_step
+    fused_flag = getattr(e2e_runner, "fused_collective", False)
+    crossrank = None
+    if world > 1:
+        # replicas must stay bit-identical: max over ranks of |flat - flat of rank 0|
+        ref_w = stack.flat.detach().clone()
+        torch.distributed.broadcast(ref_w, src=0)
+        dmax = (stack.flat.detach() - ref_w).abs().max().reshape(1).double()
+        torch.distributed.all_reduce(dmax, op=torch.distributed.ReduceOp.MAX)
+        crossrank = float(dmax.item())
+    e2e_runner_keep = e2e_runner
+    del e2e_runner
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
     clocks = sampler.summary()
 
-    # ---- roofline of the dominant kernel family ----------------------------------------------------
-    # the backward phase overlaps two kernel families on several streams, so only the serial
-    # single-family phases give a clean per-launch duration
-    kernel_phases = {"forward_logdet": ("finc::conv::conv_cta_kernel (forward)", sum(lv.n_units for lv in lvls)),
-                     "inverse": ("finc::rw::inverse_rw_kernel", sum(lv.n_units for lv in lvls))}
+    # ---- roofline of the longest phase ------------------------------------------------------------------
+    # algorithmic bytes: forward / inverse 8 B per element and unit, backward 12 (read dz, read x,
+    # write dx).  forward and inverse are serial chains of one kernel family, so phase time / launches is a clean
+    # per-launch duration; the backward phase overlaps the dX chain with the dW launches on side streams, so its
+    # `avg_launch_us` is phase time / launches (an SM-time share, not a serial duration).
+    n_units = sum(lv.n_units for lv in lvls)
+    elems = sum(lv.n_units * B * lv.dim for lv in lvls)
+    phase_info = {
+        "forward_logdet": ("finc::conv::conv_cta_kernel (forward) + gaussian_logp", n_units + len(lvls),
+                           8 * elems + sum(8 * B * lv.dim for lv in lvls)),
+        "backward": ("finc::conv::conv_cta_kernel (dX) + finc::wgrad_kernel (dW), overlapped", 2 * n_units - len(lvls),
+                     12 * elems),
+        "inverse": ("finc::rw::inverse_rw_kernel", n_units, 8 * elems),
+    }
     pm = dict(zip(HotPathRunner.PHASES, phase_ms))
-    dom = max(kernel_phases, key=lambda p: pm[p])
-    kname, nlaunch = kernel_phases[dom]
-    if dom == "forward_logdet":
-        nlaunch += len(lvls)  # + one gaussian_logp kernel per level in that phase
-    bytes_phase = sum(algorithmic_bytes(dom, lv, B) * lv.n_units for lv in lvls)
-    if dom == "forward_logdet":
-        bytes_phase += sum(8 * B * lv.dim for lv in lvls)  # gaussian_logp: read z, write dz
+    dom = max(phase_info, key=lambda p: pm[p])
+    kname, nlaunch, bytes_phase = phase_info[dom]
     avg_us = 1e3 * pm[dom] / nlaunch
     achieved = bytes_phase / nlaunch / avg_us / 1e3  # GB/s
     traffic = None
@@ -460,8 +611,16 @@ def main_ours(args):
                 "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": kname, "phase": dom,
                 "launches_per_step": nlaunch, "avg_launch_us": round(avg_us, 3),
                 "algorithmic_bytes_per_launch": bytes_phase // nlaunch, "peak_source": peak_src,
+                "all_phases": {p: {"ms": round(pm[p], 4), "frac": round(phase_info[p][2] / (pm[p] * 1e-3) / 1e9 / peak, 4)}
+                               for p in phase_info},
                 "note": "batch-256 launches move 1.6-6.3 MB each (<1 us at peak): launch/latency-bound; "
                         "see `kernels` for the same kernels streaming from HBM at batch 16384"}
+
+    extras = None
+    if not args.no_extra:
+        del e2e_runner_keep
+        torch.cuda.empty_cache()
+        extras = run_extra_workloads(torch, dev, world, rank, pg, K)
 
     line = None
     if rank == 0:
@@ -472,6 +631,7 @@ def main_ours(args):
                 whole = whole_flow_detail(torch, dev)
             except Exception as e:  # context only: never fail the bench line over it
                 whole = {"error": repr(e)}
+        gpu_ref = gpu_reference_detail(torch, dev, pm) if (world == 1 and not args.no_detail) else None
         cpu = None
         if world == 1 and not args.no_cpu:
             r = run_reference_cpu(steps=6, warmup=1, max_seconds=25.0)
@@ -480,8 +640,8 @@ def main_ours(args):
             "metric": "images/sec fwd+logdet, train step, and inverse sampling", "value": round(value, 1),
             "unit": "images/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(elapsed_ms / K, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "units_per_level": UNITS_PER_LEVEL,
-                       "kernel_size": KSIZE, "parallelism": f"dp{world} (batch sharded; train step: " + ("fused NVLink peer-memory all-reduce + Adam kernel" if getattr(e2e_runner, "fused_collective", False) else "NCCL all-reduce of the flat FInC gradient bucket") + "; sampling without collective)",
+            "config": base_config(world),
+            "config_detail": {"parallelism": f"dp{world} (batch sharded; train step: " + ("fused NVLink peer-memory all-reduce + Adam kernel" if fused_flag else "NCCL all-reduce of the flat FInC gradient bucket") + "; sampling without collective)",
                        "l2": f"{NSLOT} rotating input/activation sets (~{NSLOT * 0.2:.1f} GB total, > 126 MB L2); "
                              "intermediates of a step stay L2-resident as in a real flow",
                        "execution": "one CUDA graph per phase (forward, backward = dX chain with the dW launches fanned out over 6 side streams, optimizer, inverse); kernels launched with programmatic dependent launch"},
@@ -499,6 +659,9 @@ def main_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "crossrank_param_maxdiff": crossrank,
+            "extra_workloads": extras,
+            "gpu_reference": gpu_ref,
             "overlapped_sampling": overlap, "kernels": detail, "whole_flow_context": whole,
         }
         emit(line)
@@ -535,6 +698,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-overlap", action="store_true", help="skip the overlapped-sampling measurement")
     ap.add_argument("--no-detail", action="store_true", help="skip the per-kernel detail table")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other named configurations (extra_workloads)")
     args = ap.parse_args()
     if args.impl == "reference":
         return main_reference(args)

@@ -22,6 +22,18 @@ __device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
         if (spins > (1u << 26)) __trap();
     }
 }
+// one lane of a converged warp (the same lane every time): tcgen05.mma / tcgen05.commit / TMA issue
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

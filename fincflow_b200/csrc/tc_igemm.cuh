@@ -85,7 +85,7 @@ struct Cfg {
     static constexpr int kStages = kStagesCap > 4 ? 4 : kStagesCap;
     static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStagingBytes + 2048;
     // two-level accumulation
-    static constexpr int kFlush = NPASS == 3 ? 1 : 4;                  // k-blocks per TMEM partial
+    static constexpr int kFlush = NPASS == 3 ? 2 : 4;                  // k-blocks per TMEM partial (2: 24 MMAs, 1.5k cycles -- hides the epilogue round trip behind a ring of two)
     static constexpr int kNPartRaw = (512 - kStages * kACols) / BN;
     static constexpr int kNPart = kNPartRaw > 4 ? 4 : kNPartRaw;       // ring depth
     static constexpr int kAColBase = kNPart * BN;                      // activation stages sit behind the partials
@@ -135,7 +135,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     uint64_t* part_empty = part_full + NP;  // [NP] partial added into the running sums
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(part_empty + NP);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: the compiler then KNOWS the role branches are warp-uniform and keeps
+    // loop counters / descriptors of the single-thread roles in uniform registers (measured: with
+    // `threadIdx.x >> 5` every tcgen05.mma was preceded by ELECT + R2UR.BROADCAST sequences, ~100 issue
+    // cycles per MMA, and the MMA warp -- not the tensor core -- was the bottleneck)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t rank = CL > 1 ? cluster_ctarank() : 0;
     const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
     const int m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
@@ -170,8 +174,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     pdl_wait();  // everything above overlaps the previous kernel's tail
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+        {
             uint32_t it = 0;
             for (int ct = cluster_id; ct < cluster_tiles; ct += n_clusters) {
                 const TileCoord t = tile_coord(g, (ct / g.n_tiles) * CL + (int)rank, ct % g.n_tiles, BN);
@@ -180,25 +184,28 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                     for (int kb = 0; kb < g.kb_per_tap; ++kb, ++it) {
                         const int s = it % S;
                         mbar_wait_long(&empty[s], ((it / S) & 1) ^ 1);   // stage free in EVERY CTA of the cluster
-                        mbar_arrive_expect_tx(&full[s], kABytes + C::kParts * C::kBBytes);
-                        tma_load_4d(a_raw(s), &mapA, &full[s], kb * kBK, t.w0 + dx, t.h0 + dy, t.n0);
                         const int wrow = tap * g.n_rows + t.ncol0 + (int)rank * BNS;
-                        if (CL == 1) {
-                            tma_load_2d(b_hi(s), &mapB, &full[s], kb * kBK, wrow);
-                            if (NPASS == 3) tma_load_2d(b_lo(s), &mapB, &full[s], kb * kBK, g.taps * g.n_rows + wrow);
-                        } else {
-                            tma_load_2d_mc(b_hi(s) + rank * BNS * 128, &mapB, &full[s], kb * kBK, wrow, kAllCtas);
-                            if (NPASS == 3)
-                                tma_load_2d_mc(b_lo(s) + rank * BNS * 128, &mapB, &full[s], kb * kBK,
-                                               g.taps * g.n_rows + wrow, kAllCtas);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&full[s], kABytes + C::kParts * C::kBBytes);
+                            tma_load_4d(a_raw(s), &mapA, &full[s], kb * kBK, t.w0 + dx, t.h0 + dy, t.n0);
+                            if (CL == 1) {
+                                tma_load_2d(b_hi(s), &mapB, &full[s], kb * kBK, wrow);
+                                if (NPASS == 3) tma_load_2d(b_lo(s), &mapB, &full[s], kb * kBK, g.taps * g.n_rows + wrow);
+                            } else {
+                                tma_load_2d_mc(b_hi(s) + rank * BNS * 128, &mapB, &full[s], kb * kBK, wrow, kAllCtas);
+                                if (NPASS == 3)
+                                    tma_load_2d_mc(b_lo(s) + rank * BNS * 128, &mapB, &full[s], kb * kBK,
+                                                   g.taps * g.n_rows + wrow, kAllCtas);
+                            }
                         }
+                        __syncwarp();
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
+        {
             constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
             uint32_t it = 0, gq = 0;   // k-block counter, group (= partial) counter
             for (int ct = cluster_id; ct < cluster_tiles; ct += n_clusters) {
@@ -217,23 +224,24 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                     tc_fence_after();
                     const uint64_t db_hi = umma_desc_k_sw128(b_hi(s)), db_lo = umma_desc_k_sw128(b_lo(s));
                     const uint32_t ta_hi = tmem_base + C::kAColBase + s * C::kACols, ta_lo = ta_hi + kBK;
-                    // small terms first (a_lo*b_hi, a_hi*b_lo), the dominant product last
+                    if (elect_one()) {
+                        // small terms first (a_lo*b_hi, a_hi*b_lo), the dominant product last
 #pragma unroll
-                    for (int pass = 0; pass < NPASS; ++pass) {
+                        for (int pass = 0; pass < NPASS; ++pass) {
 #pragma unroll
-                        for (int k = 0; k < kBK / kUmmaK; ++k) {
-                            const uint64_t adv = (uint64_t)(k * kUmmaK * 4 >> 4);  // 32 bytes per K step inside the swizzle row
-                            const uint32_t acc = (in_group != 0 || pass != 0 || k != 0) ? 1u : 0u;
-                            const uint32_t ta = ((NPASS == 3 && pass == 0) ? ta_lo : ta_hi) + k * kUmmaK;
-                            const uint64_t db = (NPASS == 3 && pass == 1) ? db_lo : db_hi;
-                            umma_tf32_ts(d_tmem, ta, db + adv, idesc, acc);
+                            for (int k = 0; k < kBK / kUmmaK; ++k) {
+                                const uint64_t adv = (uint64_t)(k * kUmmaK * 4 >> 4);  // 32 bytes per K step inside the swizzle row
+                                const uint32_t acc = (in_group != 0 || pass != 0 || k != 0) ? 1u : 0u;
+                                const uint32_t ta = ((NPASS == 3 && pass == 0) ? ta_lo : ta_hi) + k * kUmmaK;
+                                const uint64_t db = (NPASS == 3 && pass == 1) ? db_lo : db_hi;
+                                umma_tf32_ts(d_tmem, ta, db + adv, idesc, acc);
+                            }
                         }
+                        if (CL == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], kAllCtas);
+                        if (in_group == C::kFlush - 1 || kblk == kblocks - 1) umma_commit(&part_full[p]);
                     }
-                    if (CL == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], kAllCtas);
-                    if (in_group == C::kFlush - 1 || kblk == kblocks - 1) {
-                        umma_commit(&part_full[p]);
-                        ++gq;
-                    }
+                    __syncwarp();
+                    if (in_group == C::kFlush - 1 || kblk == kblocks - 1) ++gq;
                 }
             }
         }

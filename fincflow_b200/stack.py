@@ -229,10 +229,19 @@ class HotPathRunner:
             self.coll_local = torch.zeros(4, dtype=torch.int32, device=self.device)
             handle.barrier()  # pads and buckets are initialised everywhere before the first step
             self._symm = (bucket, handle)
-            self.grad = bucket
-            self.fused_collective = True
+            ok = True
         except Exception as e:  # pragma: no cover - depends on the machine
             self.fused_collective_error = repr(e)
+            ok = False
+        # every rank must take the same path: one rank falling back to NCCL while its peers spin in the
+        # fused kernel would deadlock the job
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN, group=self.pg)
+        if int(flag.item()) == 1:
+            self.grad = self._symm[0]
+            self.fused_collective = True
+        elif ok:
+            self.fused_collective_error = "another rank could not set up peer memory"
 
     def _prepare_weights(self):
         """one batched launch per (level, kind); the launches are independent of each other, so they

@@ -148,3 +148,73 @@ class ReferenceCpuStack:
                     h = unit_reverse(h, w, self.pool, self.nshards)
                 samples.append(h)
         return logps, samples
+
+
+class ReferenceGpuStack:
+    """The reference's own GPU path for the same step (bench.py `gpu_reference`, tests): forward /
+    backward = torch.chunk -> F.pad -> F.conv2d -> torch.cat under autograd with TF32 off
+    (fastflow/fastflow.py:31-50, layers/conv.py:102-107; the reference's CUDA 10.2 stack predates
+    TF32), `grad * mask` (layers/conv.py:98-99), torch.optim.Adam, and sampling through
+    FastFlowUnit.reverse_level2 (fastflow/fastflow.py:78-100) on the reference's CUDA extension
+    compiled unmodified by oracle/build_ref_cuda.py: (H+W-1)*Cq launches + device syncs per unit
+    (cinc_cuda_kernel_level2.cu:98-132)."""
+
+    def __init__(self, levels, batch, device, seed=0, lr=1e-3):
+        from . import build_ref_cuda
+
+        self.ext = build_ref_cuda.load(2)
+        if self.ext is None:
+            raise RuntimeError("oracle/_ref/cinc_cuda_level2 was not built")
+        self.levels, self.B, self.device = levels, batch, torch.device(device)
+        rng = np.random.default_rng(seed)
+        self.weights, self.masks = [], []
+        for lv in levels:
+            ws = [torch.from_numpy(fo.init_unit_weight(lv.cq, lv.kernel_size, rng)).to(self.device).requires_grad_(True)
+                  for _ in range(lv.n_units)]
+            self.weights.append(ws)
+            self.masks.append(unit_mask(lv.cq, lv.kernel_size).to(self.device))
+        self.opt = torch.optim.Adam([w for ws in self.weights for w in ws], lr=lr)
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        self.x = [torch.randn(batch, lv.channels, lv.height, lv.width, generator=g, device=self.device) for lv in levels]
+        self.z = [torch.randn(batch, lv.channels, lv.height, lv.width, generator=g, device=self.device) for lv in levels]
+
+    def unit_reverse(self, z, w4):
+        """fastflow/fastflow.py:78-100"""
+        ks = [wq if not _FLIP[o] else torch.flip(wq, _FLIP[o]) for wq, o in zip(torch.chunk(w4, 4, dim=0), ORDERS)]
+        kernel = torch.cat(ks, dim=0).contiguous()
+        xs = [zq if not _FLIP[o] else torch.flip(zq, _FLIP[o]) for zq, o in zip(torch.chunk(z, 4, dim=1), ORDERS)]
+        x = torch.cat(xs, dim=1).contiguous()
+        y = torch.zeros_like(x).to(x.device)
+        y = self.ext.inverse(x, kernel, y)[0]
+        ys = [yq if not _FLIP[o] else torch.flip(yq, _FLIP[o]) for yq, o in zip(torch.chunk(y, 4, dim=1), ORDERS)]
+        return torch.cat(ys, dim=1)
+
+    def train_step(self):
+        self.opt.zero_grad(set_to_none=True)
+        for li, lv in enumerate(self.levels):
+            h = self.x[li]
+            for w in self.weights[li]:
+                h = unit_forward(h, w)
+            logp = -0.5 * h.flatten(1).pow(2).sum(1) - 0.5 * lv.dim * math.log(2 * math.pi)
+            (-logp.sum() / self.B).backward()
+        for ws, m in zip(self.weights, self.masks):
+            for w in ws:
+                w.grad = w.grad * m
+        self.opt.step()
+
+    def forward_only(self):
+        with torch.no_grad():
+            for li, lv in enumerate(self.levels):
+                h = self.x[li]
+                for w in self.weights[li]:
+                    h = unit_forward(h, w)
+
+    def sample(self):
+        out = []
+        with torch.no_grad():
+            for li in range(len(self.levels)):
+                h = self.z[li]
+                for w in reversed(self.weights[li]):
+                    h = self.unit_reverse(h, w.detach())
+                out.append(h)
+        return out

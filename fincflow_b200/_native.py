@@ -40,8 +40,8 @@ SYMBOLS = (
     "finc_squeeze_f32", "finc_unsqueeze_f32", "finc_adam_step_f32", "finc_allreduce_adam_f32", "finc_affine1x1_f32",
     "finc_affine1x1_backward_weight_workspace_bytes", "finc_affine1x1_backward_weight_f32",
     "finc_preprocess_f32", "finc_tc_conv_weights_bytes", "finc_tc_conv_prepare_weights_f32", "finc_tc_conv_nhwc_f32",
-    "finc_coupling_prepared_bytes", "finc_coupling_workspace_bytes", "finc_coupling_prepare_f32",
-    "finc_coupling_apply_f32",
+    "finc_tc_wgrad_workspace_bytes", "finc_tc_wgrad_f32", "finc_coupling_prepared_bytes", "finc_coupling_workspace_bytes", "finc_coupling_prepare_f32",
+    "finc_coupling_apply_f32", "finc_coupling_backward_workspace_bytes", "finc_coupling_backward_f32",
 )
 
 _lib = None
@@ -105,12 +105,20 @@ def load():
     lib.finc_tc_conv_prepare_weights_f32.argtypes = [p, p, i, i, i, i, p]
     lib.finc_tc_conv_nhwc_f32.restype = i
     lib.finc_tc_conv_nhwc_f32.argtypes = [p, p, p, p, p, i, i, i, i, i, i, i, u, p]
+    lib.finc_tc_wgrad_workspace_bytes.restype = sz
+    lib.finc_tc_wgrad_workspace_bytes.argtypes = [ctypes.c_long, i, i]
+    lib.finc_tc_wgrad_f32.restype = i
+    lib.finc_tc_wgrad_f32.argtypes = [p, p, p, p, sz, ctypes.c_long, i, i, i, i, i, u, p]
     lib.finc_coupling_prepared_bytes.restype = sz
-    lib.finc_coupling_prepared_bytes.argtypes = [i, i]
+    lib.finc_coupling_prepared_bytes.argtypes = [i, i, i]
     lib.finc_coupling_workspace_bytes.restype = sz
     lib.finc_coupling_workspace_bytes.argtypes = [i, i, i, i, i]
     lib.finc_coupling_prepare_f32.restype = i
-    lib.finc_coupling_prepare_f32.argtypes = [p] * 7 + [ctypes.c_float, p, i, i, p]
+    lib.finc_coupling_prepare_f32.argtypes = [p] * 7 + [ctypes.c_float, p, i, i, i, p]
+    lib.finc_coupling_backward_workspace_bytes.restype = sz
+    lib.finc_coupling_backward_workspace_bytes.argtypes = [i, i, i, i, i]
+    lib.finc_coupling_backward_f32.restype = i
+    lib.finc_coupling_backward_f32.argtypes = [p] * 6 + [sz] + [p] * 8 + [i, i, i, i, i, u, p]
     lib.finc_coupling_apply_f32.restype = i
     lib.finc_coupling_apply_f32.argtypes = [p, p, p, p, p, sz, i, i, i, i, i, i, u, p]
     for f in ("finc_set_device", "finc_forward_f32", "finc_backward_input_f32", "finc_backward_weight_f32",
@@ -443,27 +451,83 @@ def tc_conv_nhwc(x, wprep, bias, Npad, taps, relu=False, relu_mask=None, flags=0
     return y
 
 
-def coupling_prepared_bytes(C, width) -> int:
+def tc_wgrad(P, Q, M=None, N=None, flags=0, out=None):
+    """dW[m, n] = sum_p P[p, m] * Q[p, n] for channels-last activations P [..., ldP], Q [..., ldQ]"""
+    P, Q = _prep(P, "P"), _prep(Q, "Q")
+    _bind_device(P)
+    ldP, ldQ = int(P.shape[-1]), int(Q.shape[-1])
+    M = ldP if M is None else M
+    N = ldQ if N is None else N
+    npix = P.numel() // ldP
+    nbytes = load().finc_tc_wgrad_workspace_bytes(npix, M, N)
+    if nbytes == 0:
+        raise FincNativeError(f"tc_wgrad: N={N} not covered (multiple of 64 needed)")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=P.device)
+    dW = torch.empty((M, N), dtype=torch.float32, device=P.device) if out is None else out
+    _check(load().finc_tc_wgrad_f32(P.data_ptr(), Q.data_ptr(), dW.data_ptr(), ws.data_ptr(), ws.numel(), npix, M, N,
+                                    ldP, ldQ, int(dW.stride(0)), flags, _stream(P)), "finc_tc_wgrad_f32", 2)
+    return dW
+
+
+def coupling_prepared_bytes(C, width, with_backward=False) -> int:
     """bytes of the prepared weight blob of one Coupling layer; 0 = not covered by the tensor-core path"""
-    return int(load().finc_coupling_prepared_bytes(C, width))
+    return int(load().finc_coupling_prepared_bytes(C, width, int(with_backward)))
 
 
 def coupling_workspace_bytes(B, C, H, W, width) -> int:
     return int(load().finc_coupling_workspace_bytes(B, C, H, W, width))
 
 
-def coupling_prepare(w1, b1, w2, b2, w3, b3, logs3, logscale_factor=3.0, out=None):
-    """weights of Coupling.net (layers/coupling.py:56-66) -> one prepared blob (uint8 tensor)"""
+def coupling_prepare(w1, b1, w2, b2, w3, b3, logs3, logscale_factor=3.0, out=None, with_backward=False):
+    """weights of Coupling.net (layers/coupling.py:56-66) -> one prepared blob (uint8 tensor);
+    with_backward adds the transposed weights the backward pass needs"""
     ts = [_prep(t, "coupling parameter") for t in (w1, b1, w2, b2, w3, b3, logs3)]
     _bind_device(ts[0])
     C, width = int(w3.shape[0]), int(w1.shape[0])
-    nbytes = coupling_prepared_bytes(C, width)
+    nbytes = coupling_prepared_bytes(C, width, with_backward)
     if nbytes == 0:
         raise FincNativeError(f"coupling_prepare: C={C}, width={width} not covered by the tensor-core path")
-    blob = torch.empty(nbytes, dtype=torch.uint8, device=ts[0].device) if out is None else out
+    blob = out if (out is not None and out.numel() == nbytes) else torch.empty(nbytes, dtype=torch.uint8, device=ts[0].device)
     _check(load().finc_coupling_prepare_f32(*[t.data_ptr() for t in ts], float(logscale_factor), blob.data_ptr(),
-                                            C, width, _stream(ts[0])), "finc_coupling_prepare_f32", 4)
+                                            C, width, int(with_backward), _stream(ts[0])), "finc_coupling_prepare_f32",
+           5 if with_backward else 4)
     return blob
+
+
+_scratch = {}
+
+
+def _shared_scratch(nbytes, device):
+    """one transient scratch buffer per device, grown on demand (stream-ordered reuse)"""
+    buf = _scratch.get(device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _scratch[device] = buf
+    return buf
+
+
+def coupling_backward(x, dy, dlogdet, blob, fwd_workspace, width, flags=0):
+    """(dx, dw1, db1, dw2, db2, dw3, db3, dlogs3) of coupling_apply(forward); `blob` prepared with_backward"""
+    x, dy = _prep(x, "x"), _prep(dy, "dy")
+    _bind_device(x)
+    B, C, H, W = (int(v) for v in x.shape)
+    nbytes = int(load().finc_coupling_backward_workspace_bytes(B, C, H, W, width))
+    if nbytes == 0:
+        raise FincNativeError(f"coupling_backward: shape {tuple(x.shape)}, width {width} not covered")
+    scratch = _shared_scratch(nbytes, x.device)
+    f = dict(dtype=torch.float32, device=x.device)
+    dx = torch.empty_like(x)
+    dw1, db1 = torch.empty((width, C // 2, 3, 3), **f), torch.empty(width, **f)
+    dw2, db2 = torch.empty((width, width, 1, 1), **f), torch.empty(width, **f)
+    dw3, db3, dlogs3 = torch.empty((C, width, 3, 3), **f), torch.empty(C, **f), torch.empty(C, **f)
+    if dlogdet is not None:
+        dlogdet = _prep(dlogdet, "dlogdet")
+    _check(load().finc_coupling_backward_f32(x.data_ptr(), dy.data_ptr(), None if dlogdet is None else dlogdet.data_ptr(),
+                                             blob.data_ptr(), fwd_workspace.data_ptr(), scratch.data_ptr(), scratch.numel(),
+                                             dx.data_ptr(), dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), db2.data_ptr(),
+                                             dw3.data_ptr(), db3.data_ptr(), dlogs3.data_ptr(), B, C, H, W, width, flags,
+                                             _stream(x)), "finc_coupling_backward_f32", 24)
+    return dx, dw1, db1, dw2, db2, dw3, db3, dlogs3
 
 
 def coupling_apply(x, blob, width, reverse=False, want_logdet=True, logdet_out=None, flags=0, out=None, workspace=None):

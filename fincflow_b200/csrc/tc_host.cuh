@@ -13,6 +13,12 @@ int launch_igemm_nhwc(int BN, int npass, int cluster, const CUtensorMap& mapA, c
 int launch_igemm_rows(int BN, int npass, const CUtensorMap& mapA, const CUtensorMap& mapB, const Geom& g,
                       const EpiArgs& e, cudaStream_t st);
 
+struct WgradGeom;
+int launch_wgrad(int BN, int npass, const CUtensorMap& mapP, const CUtensorMap& mapQ, float* out, const WgradGeom& g,
+                 cudaStream_t st);
+int launch_wgrad_reduce(const float* partial, float* dst, int M, int N, int ld_src, size_t slice_stride, int slices,
+                        int ld_dst, int accumulate, cudaStream_t st);
+
 template <int BN, int NPASS, int EPI, int CL, int EW>
 inline int launch_igemm_t(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapOut, const Geom& g,
                           const EpiArgs& e, cudaStream_t st) {

@@ -114,6 +114,13 @@ class LogitTransform(PreprocessingFlowLayer):
 
 
 class ActNorm(FlowLayer):
+    """layers/actnorm.py:14-64.  `sync_init`: under torch.distributed the data-dependent initialisation uses
+    the moments of the GLOBAL batch (all-reduced count / sum / sum of squares), so that every replica of a
+    data-parallel job starts with the same translation / log_scale (the reference initialises from
+    replica 0's shard inside nn.DataParallel: layers/actnorm.py:17-23)."""
+
+    sync_init = True
+
     def __init__(self, n_dims):
         super().__init__()
         self.n_dims = n_dims
@@ -121,12 +128,29 @@ class ActNorm(FlowLayer):
         self.log_scale = nn.Parameter(torch.zeros(n_dims))
         self.register_buffer("initialized", torch.tensor(0))
 
+    @staticmethod
+    def _moments(input):
+        dims = [0, 2, 3]
+        import torch.distributed as dist
+
+        if ActNorm.sync_init and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            n = torch.tensor([float(input.numel() // input.shape[1])], device=input.device, dtype=torch.float64)
+            s = input.double().sum(dim=dims)
+            ss = input.double().pow(2).sum(dim=dims)
+            packed = torch.cat([n, s, ss])
+            dist.all_reduce(packed)
+            n, s, ss = packed[0], packed[1:1 + s.numel()], packed[1 + s.numel():]
+            mean = s / n
+            var = (ss - n * mean * mean) / (n - 1)          # unbiased, like torch.std
+            return mean.to(input.dtype), var.clamp_min(0).sqrt().to(input.dtype)
+        return input.mean(dim=dims), input.std(dim=dims)
+
     def forward(self, input, context=None):
         if not self.initialized:  # data-dependent init on the first batch (actnorm.py:17-23)
             with torch.no_grad():
-                dims = [0, 2, 3]
-                self.translation.data.copy_(input.mean(dim=dims))
-                self.log_scale.data.copy_(torch.log(input.std(dim=dims) + 1e-8))
+                mean, std = self._moments(input)
+                self.translation.data.copy_(mean)
+                self.log_scale.data.copy_(torch.log(std + 1e-8))
                 self.initialized.fill_(1)
         t, ls = self.translation.view(1, -1, 1, 1), self.log_scale.view(1, -1, 1, 1)
         return (input - t) * torch.exp(-ls), self.logdet(input, context)
@@ -205,15 +229,17 @@ class Coupling(FlowLayer):
         return (self.tensor_core and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
                 and _native.coupling_prepared_bytes(self.n_channels, self.width) > 0)
 
-    def prepared(self):
+    def prepared(self, with_backward=False):
         """hi / lo split weight blob, rebuilt only when a parameter changed (in-place updates bump
-        `_version`; optimizers and load_state_dict do)"""
+        `_version`; optimizers and load_state_dict do).  `with_backward` adds the transposed weights of
+        the backward pass."""
         ps = self._params()
-        key = tuple((p.data_ptr(), p._version) for p in ps)
+        key = (with_backward,) + tuple((p.data_ptr(), p._version) for p in ps)
         if self._blob is None or key != self._blob_key or self._blob.device != ps[0].device:
             self._blob = _native.coupling_prepare(*[p.detach() for p in ps], self.net[4].logscale_factor,
                                                   out=self._blob if self._blob is not None
-                                                  and self._blob.device == ps[0].device else None)
+                                                  and self._blob.device == ps[0].device else None,
+                                                  with_backward=with_backward)
             self._blob_key = key
         return self._blob
 
@@ -244,20 +270,36 @@ class Coupling(FlowLayer):
 
 
 class _CouplingFn(torch.autograd.Function):
-    """Coupling.forward on the tensor-core kernels; backward recomputes through the PyTorch formulas
-    (the backward kernels are the next step of this row)."""
+    """Coupling.forward and its backward on the tensor-core kernels (finc_coupling_apply_f32 /
+    finc_coupling_backward_f32).  The forward keeps its workspace (the channels-last hidden activations)
+    for the backward.  Widths the backward kernels do not cover (width % 128 != 0) recompute through the
+    PyTorch formulas instead."""
 
     @staticmethod
     def forward(ctx, x, module, *params):
         ctx.module = module
+        B, C, H, W = x.shape
+        train = any(ctx.needs_input_grad)
+        ctx.native = train and _native.coupling_prepared_bytes(C, module.width, True) > 0
+        ws = None
+        if ctx.native:
+            ws = torch.empty(_native.coupling_workspace_bytes(B, C, H, W, module.width), dtype=torch.uint8, device=x.device)
+        blob = module.prepared(with_backward=ctx.native)
+        y, logdet = _native.coupling_apply(x, blob, module.width, flags=module._flags(), workspace=ws)
         ctx.save_for_backward(x)
-        y, logdet = _native.coupling_apply(x, module.prepared(), module.width, flags=module._flags())
+        ctx.ws, ctx.blob = ws, blob
         return y, logdet
 
     @staticmethod
     def backward(ctx, dy, dlogdet):
         (x,) = ctx.saved_tensors
         m = ctx.module
+        if ctx.native:
+            if dy is None:
+                dy = torch.zeros_like(x)
+            grads = _native.coupling_backward(x, dy.contiguous(), dlogdet, ctx.blob, ctx.ws, m.width, flags=m._flags())
+            ctx.ws = None
+            return (grads[0], None, *grads[1:])
         ps = m._params()
         with torch.enable_grad():
             xi = x.detach().requires_grad_(ctx.needs_input_grad[0])

@@ -1,0 +1,129 @@
+"""Data-parallel training of a whole flow: one process per GPU, batch sharded, gradients all-reduced.
+
+What the reference's multi-GPU scripts do with nn.DataParallel (fastflow_cifar_multi_gpu.py:392-451,
+train/experiment.py:219-277: scatter the batch, replicate the model every step, gather outputs on GPU 0,
+reduce gradients to GPU 0, step there) done the torch.distributed way:
+
+  * every rank holds a replica and its shard of the batch; the loss is the reference's
+    `-(log p).sum() / B_global` (train/experiment.py:198-206) so that summed gradients equal the
+    single-process gradient;
+  * all gradients live in ONE flat fp32 buffer (each `p.grad` is a view into it), cut into buckets in
+    reverse parameter order; a bucket's NCCL all-reduce is launched from the autograd hook of its last
+    parameter, so the collective of the late layers overlaps the backward of the early ones
+    (the CIFAR-10 flow has 22.9 M parameters = 91 MB of gradients);
+  * the FInC gradient mask is applied inside the weight-gradient kernel (mask_in_backward=True), i.e.
+    before the all-reduce -- masked entries are exactly zero on every rank;
+  * ActNorm's data-dependent initialisation uses the statistics of the GLOBAL batch (flows.ActNorm
+    all-reduces count / sum / sum of squares), so replicas start identical (the reference initialises on
+    replica 0's shard: layers/actnorm.py:17-23);
+  * sampling and likelihood evaluation use no collective.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class FlowTrainer:
+    def __init__(self, model, lr=1e-3, process_group=None, bucket_mb=25.0, optimizer=None, grad_clip_norm=None):
+        self.model = model
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
+        if self.world > 1 and self.pg is None:
+            self.pg = dist.group.WORLD
+        self.grad_clip_norm = grad_clip_norm
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self._build_buckets(bucket_mb)
+        self.optimizer = optimizer if optimizer is not None else self._make_adam(lr)
+        if self.world > 1:
+            self.broadcast_parameters()
+
+    # ---- flat gradient buffer + buckets -----------------------------------------------------------
+    def _build_buckets(self, bucket_mb):
+        dev, dt = self.params[0].device, self.params[0].dtype
+        total = sum(p.numel() for p in self.params)
+        self.flat_grad = torch.zeros(total, dtype=dt, device=dev)
+        # offsets in REVERSE parameter order: the last layers' gradients are ready first
+        self.offsets = {}
+        off = 0
+        order = list(reversed(self.params))
+        for p in order:
+            self.offsets[p] = off
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        limit = max(int(bucket_mb * 1024 * 1024 / self.flat_grad.element_size()), 1)
+        self.buckets, start, members = [], 0, []
+        for p in order:
+            members.append(p)
+            end = self.offsets[p] + p.numel()
+            if end - start >= limit:
+                self.buckets.append((start, end, members))
+                start, members = end, []
+        if members:
+            self.buckets.append((start, total, members))
+        self._bucket_of = {p: i for i, (_, _, ms) in enumerate(self.buckets) for p in ms}
+        self._pending = [0] * len(self.buckets)
+        self._works = []
+        if self.world > 1:
+            for p in self.params:
+                p.register_post_accumulate_grad_hook(self._on_grad_ready)
+
+    def _make_adam(self, lr):
+        try:
+            return torch.optim.Adam(self.params, lr=lr, fused=self.params[0].is_cuda)
+        except (TypeError, RuntimeError):
+            return torch.optim.Adam(self.params, lr=lr)
+
+    def _on_grad_ready(self, p):
+        i = self._bucket_of[p]
+        self._pending[i] -= 1
+        if self._pending[i] == 0:
+            a, b, _ = self.buckets[i]
+            self._works.append(dist.all_reduce(self.flat_grad[a:b], group=self.pg, async_op=True))
+
+    def broadcast_parameters(self, src=0):
+        """one-time sync: replicas start from rank `src`'s parameters and buffers"""
+        for t in list(self.model.parameters()) + list(self.model.buffers()):
+            dist.broadcast(t.data, src=src, group=self.pg)
+
+    # ---- one optimisation step ----------------------------------------------------------------------
+    def step(self, x):
+        """x = this rank's shard.  Returns the global mean negative log-likelihood (a 0-dim tensor)."""
+        self.flat_grad.zero_()
+        for p in self.params:  # autograd must accumulate into the bucket views
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + self.offsets[p] * self.flat_grad.element_size():
+                p.grad = self.flat_grad[self.offsets[p]:self.offsets[p] + p.numel()].view_as(p)
+        self._pending = [len(ms) for _, _, ms in self.buckets]
+        self._works = []
+        _, logp = self.model(x)
+        logp = torch.nan_to_num(logp, nan=0.0)           # train/experiment.py:201-204
+        loss = -logp.sum() / (x.shape[0] * self.world)
+        loss.backward()
+        for w in self._works:
+            w.wait()
+        if self.world > 1 and any(n != 0 for n in self._pending):
+            # parameters that received no gradient this step: reduce their buckets now (zeros stay zeros)
+            for i, n in enumerate(self._pending):
+                if n != 0:
+                    a, b, _ = self.buckets[i]
+                    dist.all_reduce(self.flat_grad[a:b], group=self.pg)
+        if self.grad_clip_norm is not None:
+            torch.nn.utils.clip_grad_norm_(self.params, self.grad_clip_norm)
+        self.optimizer.step()
+        if self.world > 1:
+            loss = loss.detach().clone()
+            dist.all_reduce(loss, group=self.pg)
+        return loss.detach()
+
+    # ---- checks ---------------------------------------------------------------------------------------
+    def replica_max_diff(self):
+        """max |parameter - rank 0's parameter| over all parameters and ranks (must be 0)"""
+        if self.world == 1:
+            return 0.0
+        worst = torch.zeros((), dtype=torch.float64, device=self.params[0].device)
+        for p in self.params:
+            ref = p.detach().clone()
+            dist.broadcast(ref, src=0, group=self.pg)
+            worst = torch.maximum(worst, (p.detach() - ref).abs().max().double())
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=self.pg)
+        return float(worst.item())

@@ -234,6 +234,16 @@ int finc_tc_conv_prepare_weights_f32(const float* w, void* prepared, int N, int 
 int finc_tc_conv_nhwc_f32(const float* x, const void* prepared, const float* bias, const float* relu_mask, float* y,
                           int B, int H, int W, int Cin_pad, int Npad, int taps, int relu, unsigned flags, void* stream);
 
+/* Weight-gradient GEMM on the tensor cores (reduction over pixels, deterministic split-K):
+ *   dW[m, n] (+)= sum_p P[p, m] * Q[p, n]     P: [np, ldP], Q: [np, ldQ] channels-last fp32, dW: [M, ld_dW]
+ * P = gradient at a convolution's output, Q = its (im2col-form) input.  N must be a multiple of 64
+ * (128 / 160 preferred), ldP and ldQ multiples of 4; FINC_FLAG_ACCUMULATE adds into dW,
+ * FINC_FLAG_TF32_1PASS selects single-pass TF32.  Replaces the cuDNN wgrad autograd runs for the
+ * Coupling network's nn.Conv2d layers (fastflow/layers/coupling.py:56-66). */
+size_t finc_tc_wgrad_workspace_bytes(long np, int M, int N);
+int finc_tc_wgrad_f32(const float* P, const float* Q, float* dW, void* workspace, size_t workspace_bytes,
+                      long np, int M, int N, int ldP, int ldQ, int ld_dW, unsigned flags, void* stream);
+
 /* Affine coupling layer (fastflow/layers/coupling.py:44-105) in four launches:
  *   h = Conv2dZero(relu(conv1x1(relu(conv3x3(x[:, :C/2])))));  log_s = 2 tanh(h[:, ::2] / 2);  t = h[:, 1::2]
  *   forward:  y = cat(x1, x2 * exp(log_s) + t),   logdet[n] (+)= sum log_s        (Coupling.forward)
@@ -243,14 +253,27 @@ int finc_tc_conv_nhwc_f32(const float* x, const void* prepared, const float* bia
  * [width,width,1,1], net.2.bias, net.4.weight [C,width,3,3], net.4.bias, net.4.logs, logscale_factor).
  * finc_coupling_prepared_bytes returns 0 for shapes the path does not cover
  * (C even, round_up(C,16) in {16,32,48,64,96}, width % 32 == 0). */
-size_t finc_coupling_prepared_bytes(int C, int width);
+size_t finc_coupling_prepared_bytes(int C, int width, int with_backward);
 size_t finc_coupling_workspace_bytes(int B, int C, int H, int W, int width);
 int finc_coupling_prepare_f32(const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
                               const float* b3, const float* logs3, float logscale_factor, void* prepared,
-                              int C, int width, void* stream);
+                              int C, int width, int with_backward, void* stream);
 int finc_coupling_apply_f32(const float* x, float* y, float* logdet, const void* prepared, void* workspace,
                             size_t workspace_bytes, int B, int C, int H, int W, int width, int reverse,
                             unsigned flags, void* stream);
+
+/* Backward of finc_coupling_apply_f32 (forward direction): given dy = dL/dy and dlogdet = dL/dlogdet [B] (may be
+ * NULL) it produces dx and the gradients of the seven parameters (same shapes as the parameters).
+ * `forward_workspace` is the workspace the forward call filled (it holds the hidden activations) and `prepared`
+ * a blob made with with_backward = 1 (it carries the transposed weights).  Eleven GEMM-class launches on the
+ * tensor cores (three weight-gradient GEMMs over the pixels, three backward-data GEMMs) plus small
+ * deterministic reductions; no floating-point atomics.  width % 128 == 0.  Replaces the autograd graph of
+ * Coupling.forward (fastflow/layers/coupling.py:85-90; cuDNN dgrad / wgrad). */
+size_t finc_coupling_backward_workspace_bytes(int B, int C, int H, int W, int width);
+int finc_coupling_backward_f32(const float* x, const float* dy, const float* dlogdet, const void* prepared,
+                               const void* forward_workspace, void* scratch, size_t scratch_bytes, float* dx,
+                               float* dw1, float* db1, float* dw2, float* db2, float* dw3, float* db3, float* dlogs3,
+                               int B, int C, int H, int W, int width, unsigned flags, void* stream);
 
 /* Debug aid, inactive unless the environment has FINC_DEBUG_TS=1: the tiled kernels then record
  * per-CTA %globaltimer marks (8 slots per CTA); this call synchronises the device and copies them. */

@@ -108,3 +108,78 @@ def test_plan_host_cores():
     assert len({c for g in got for c in g}) == 16
     # more ranks than CPUs on a node: fall back to the even split of the allowed set
     assert plan_host_cores(1, 4, range(4), [0, 0, 0, 0], {0: [0, 1]}) == [1]
+
+
+# ---- whole-flow data-parallel trainer (fincflow_b200/train.py) on a CPU toy flow ----------------------------
+class _ToyFlow(torch.nn.Module):
+    """ActNorm (data-dependent init) + an elementwise affine 'flow': forward(x) -> (z, logp[B])"""
+
+    def __init__(self):
+        super().__init__()
+        from fincflow_b200.flows import ActNorm
+
+        self.act = ActNorm(3)
+        self.log_a = torch.nn.Parameter(torch.tensor([0.1, -0.2, 0.3]))
+        self.b = torch.nn.Parameter(torch.zeros(3))
+        self.unused = torch.nn.Parameter(torch.ones(2))      # never receives a gradient
+
+    def forward(self, x):
+        h, ld = self.act(x)
+        z = h * torch.exp(self.log_a).view(1, 3, 1, 1) + self.b.view(1, 3, 1, 1)
+        ld = ld + self.log_a.sum() * x.shape[2] * x.shape[3]
+        return z, -0.5 * z.flatten(1).pow(2).sum(1) + ld
+
+
+def _toy_batch():
+    g = torch.Generator().manual_seed(5)
+    return torch.randn(8, 3, 4, 4, generator=g) * 2.0 + 1.0
+
+
+def _trainer_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from fincflow_b200.train import FlowTrainer
+
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo")
+    torch.manual_seed(100 + rank)                              # replicas start DIFFERENT: the trainer must sync them
+    model = _ToyFlow()
+    with torch.no_grad():
+        model.b.add_(torch.randn(3))
+    trainer = FlowTrainer(model, lr=1e-2, bucket_mb=1e-5)      # tiny buckets: several all-reduces per step
+    assert len(trainer.buckets) >= 3
+    x = _toy_batch()
+    shard = x[rank * 4:(rank + 1) * 4]
+    losses = [float(trainer.step(shard)) for _ in range(3)]
+    diff = trainer.replica_max_diff()
+    if rank == 0:
+        out.put((losses, diff, {k: v.numpy().copy() for k, v in model.state_dict().items()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flow_trainer_two_ranks_equals_single_process():
+    from fincflow_b200.train import FlowTrainer
+
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_trainer_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    losses, diff, sd = out.get()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert diff == 0.0                                          # replicas bit-identical after three steps
+    # single process on the full batch, starting from rank 0's initial parameters
+    torch.manual_seed(100)
+    model = _ToyFlow()
+    with torch.no_grad():
+        model.b.add_(torch.randn(3))
+    trainer = FlowTrainer(model, lr=1e-2)
+    x = _toy_batch()
+    want = [float(trainer.step(x)) for _ in range(3)]
+    assert np.allclose(losses, want, rtol=1e-5)
+    for k, v in model.state_dict().items():
+        assert np.allclose(sd[k], v.numpy(), rtol=1e-5, atol=1e-6), k   # incl. ActNorm initialised from the GLOBAL batch

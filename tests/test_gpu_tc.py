@@ -158,3 +158,52 @@ def test_coupling_autograd_matches_pytorch_path():
     want = [x.grad] + [p.grad for p in cp.parameters()]
     for a, b in zip(got, want):
         assert _relmax(a, b) <= 1e-5
+
+
+@pytest.mark.parametrize("case", [(4096, 128, 64), (4096, 512, 128), (5000, 512, 160), (65536, 512, 512), (1000, 256, 320),
+                                  (33, 128, 448)])
+@pytest.mark.parametrize("npass", [3, 1])
+def test_tc_wgrad_matches_fp64_matmul(case, npass):
+    """dW[m, n] = sum_p P[p, m] Q[p, n] (reduction over pixels, split-K, fixed-order slice sum)"""
+    from fincflow_b200 import _native
+
+    npix, M, N = case
+    torch.manual_seed(npix + M)
+    P = torch.randn(npix, M, device="cuda")
+    Q = torch.randn(npix, N, device="cuda")
+    flags = _native.FLAG_TF32_1PASS if npass == 1 else 0
+    dW = _native.tc_wgrad(P, Q, flags=flags)
+    ref = P.double().t() @ Q.double()
+    assert _relmax(dW, ref) <= (2e-3 if npass == 1 else 2e-6)
+    assert torch.equal(dW, _native.tc_wgrad(P, Q, flags=flags))      # deterministic
+
+
+@pytest.mark.parametrize("case", [(4, 12, 16, 16, 128), (3, 24, 8, 8, 256), (5, 48, 4, 4, 128), (2, 4, 14, 14, 128),
+                                  (2, 96, 4, 4, 128), (8, 12, 16, 16, 512)])
+def test_coupling_native_backward_matches_pytorch_autograd(case):
+    """finc_coupling_backward_f32 (three weight-gradient GEMMs, three backward-data GEMMs, pointwise part,
+    col2im) against autograd through the PyTorch formulas, fp32 with TF32 off"""
+    from fincflow_b200 import _native
+    from fincflow_b200.flows import Coupling
+
+    B, C, H, W, width = case
+    assert _native.coupling_prepared_bytes(C, width, True) > 0
+    cp = _coupling(C, H, W, width, seed=11)
+    x = torch.randn(B, C, H, W, device="cuda", requires_grad=True)
+    gy, gl = torch.randn(B, C, H, W, device="cuda"), torch.randn(B, device="cuda")
+    y, ld = cp(x)
+    ((y * gy).sum() + (ld * gl).sum()).backward()
+    got = [x.grad.clone()] + [p.grad.clone() for p in cp.parameters()]
+    x.grad = None
+    cp.zero_grad()
+    Coupling.tensor_core = False
+    try:
+        y, ld = cp(x)
+        ((y * gy).sum() + (ld * gl).sum()).backward()
+    finally:
+        Coupling.tensor_core = True
+    want = [x.grad] + [p.grad for p in cp.parameters()]
+    names = ["dx"] + [n for n, _ in cp.named_parameters()]
+    for name, a, b in zip(names, got, want):
+        assert a.shape == b.shape, name
+        assert _relmax(a, b) <= 2e-5, (name, _relmax(a, b))

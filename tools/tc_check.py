@@ -19,6 +19,9 @@ CASES = [
     "conv:2,16,16,32,32,1,1", "conv:2,16,16,32,32,1,3", "conv:2,16,16,64,256,1,1", "conv:2,16,16,64,256,1,3",
     "conv:2,16,16,64,32,9,3", "conv:3,14,14,32,64,9,3", "conv:5,7,7,96,128,9,3", "conv:9,4,4,64,64,9,3",
     "conv:2,32,32,32,32,9,3", "conv:8,16,16,512,512,1,3", "conv:8,16,16,512,512,1,1", "conv:300,8,8,512,512,1,3",
+    # wgrad: np,M,N,npass   dW[m,n] = sum_p P[p,m] Q[p,n]
+    "wgrad:4096,128,64,3", "wgrad:4096,512,128,3", "wgrad:5000,512,160,3", "wgrad:65536,512,512,3", "wgrad:65536,512,512,1",
+    "wgrad:65536,512,64,3", "wgrad:65536,512,160,3",
     # coupling: B,C,H,W,width,npass
     "coupling:4,12,16,16,512,3", "coupling:4,12,16,16,512,1", "coupling:6,24,8,8,512,3", "coupling:9,48,4,4,512,3",
     "coupling:3,4,14,14,64,3", "coupling:3,8,7,7,64,3", "coupling:2,96,4,4,512,3", "coupling:2,12,32,32,512,3",
@@ -62,6 +65,42 @@ def run_case(spec):
             print("   first bad (b,h,w,n):", idx)
             print("   bad per n%32:", d.sum(dim=(0, 1, 2)).view(-1, 32).sum(0).tolist() if N % 32 == 0 else "")
             print("   bad per (h,w):", d.sum(dim=(0, 3)).tolist() if H * W <= 64 else d.sum(dim=(0, 2, 3)).tolist())
+        return err < (2e-3 if npass == 1 else 2e-6)
+    if kind == "wgrad":
+        npix, M, N, npass = a
+        P = torch.randn(npix, M, device=dev)
+        Q = torch.randn(npix, N, device=dev)
+        flags = _native.FLAG_TF32_1PASS if npass == 1 else 0
+        dW = _native.tc_wgrad(P, Q, flags=flags)
+        torch.cuda.synchronize()
+        ref = P.double().t() @ Q.double()
+        err = float((dW.double() - ref).abs().max() / ref.abs().max())
+        torch.backends.cuda.matmul.allow_tf32 = False
+        r32 = P.t() @ Q
+        err32 = float((r32.double() - ref).abs().max() / ref.abs().max())
+        bad = int(((dW.double() - ref).abs() > 1e-2 * ref.abs().max()).sum())
+        n = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            _native.tc_wgrad(P, Q, flags=flags, out=dW)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        e0.record()
+        for _ in range(n):
+            torch.matmul(P.t(), Q, out=r32)
+        e1.record()
+        torch.cuda.synchronize()
+        ms32 = e0.elapsed_time(e1) / n
+        fl = 2.0 * npix * M * N
+        print(f"{spec}: max-norm rel err {err:.3e} (cuBLAS fp32: {err32:.3e}), elements off by >1%: {bad} of {ref.numel()}; "
+              f"{ms * 1e3:.1f} us = {fl / ms / 1e9:.1f} TFLOP/s (cuBLAS fp32 {ms32 * 1e3:.1f} us)")
+        if bad:
+            d = (dW.double() - ref).abs() > 1e-2 * ref.abs().max()
+            print("   bad rows (m) count per 32:", d.sum(1).view(-1, 32).sum(1).tolist()[:16])
+            print("   bad cols (n) count per 16:", d.sum(0).view(-1, 16).sum(1).tolist()[:16])
+            print("   sample ours/ref:", dW[0, :6].tolist(), ref[0, :6].tolist())
         return err < (2e-3 if npass == 1 else 2e-6)
     B, C, H, W, width, npass = a
     from fincflow_b200.flows import Coupling

@@ -67,13 +67,13 @@ class FlowSequential(nn.Module):
 
     # ---- one layer, with the reference's dispatch on ModifiedGradFlowLayer --------------------
     @staticmethod
-    def _apply(module, x, context, compute_expensive):
+    def _forward_one(module, x, context, compute_expensive):
         if isinstance(module, ModifiedGradFlowLayer):
             return module(x, context, compute_expensive=compute_expensive)
         return module(x, context)
 
     @staticmethod
-    def _unapply(module, x, context, compute_expensive):
+    def _reverse_one(module, x, context, compute_expensive):
         if isinstance(module, ModifiedGradFlowLayer):
             out = module.reverse(x, context, compute_expensive)
         else:
@@ -85,7 +85,7 @@ class FlowSequential(nn.Module):
     def _push(self, modules, x, context, compute_expensive):
         logdet = 0
         for module in modules:
-            x, layer_logdet = self._apply(module, x, context, compute_expensive)
+            x, layer_logdet = self._forward_one(module, x, context, compute_expensive)
             logdet = logdet + layer_logdet
         return x, logdet
 
@@ -118,7 +118,7 @@ class FlowSequential(nn.Module):
 
     def _pull(self, z, context, compute_expensive):
         for module in reversed(self.sequence_modules):
-            z = self._unapply(module, z, context, compute_expensive)
+            z = self._reverse_one(module, z, context, compute_expensive)
         return z
 
     def sample(self, n_samples, context=None, compute_expensive=False, also_true_inverse=False):

@@ -26,9 +26,11 @@ def _ref(level):
 
 
 def _elementwise_ok(a, b, rtol=1e-5):
-    """|a - b| <= rtol * (|b| + 0.01 max|b|): element-wise relative with a small absolute floor"""
+    """|a - b| <= rtol * (|b| + 0.1 max|b|): element-wise relative with an absolute floor of 1e-6 max|b|
+    (two fp32 evaluations of the recurrence in different orders differ by a few 1e-7 absolute on
+    elements that cancel to ~0, whatever their magnitude)"""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
-    return bool((np.abs(a - b) <= rtol * (np.abs(b) + 1e-2 * np.abs(b).max())).all())
+    return bool((np.abs(a - b) <= rtol * (np.abs(b) + 1e-1 * np.abs(b).max())).all())
 
 
 def _reference_unit_reverse(ext, unit, z):

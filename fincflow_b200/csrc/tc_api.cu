@@ -153,8 +153,9 @@ __global__ void split_weights_kernel(const float* __restrict__ w, float* __restr
         } else {
             if (n < Cin && c < N) v = w[((long)c * Cin + n) * taps + (taps - 1 - tap)];
         }
-        out[idx] = v;   // raw fp32: the kernels split hi / lo on the fly (part 1 is kept for layout compatibility)
-        out[per_part + idx] = v - tf32_rn(v);
+        const float hi = tf32_rn(v);
+        out[idx] = hi;
+        out[per_part + idx] = tf32_rn(v - hi);
     }
 }
 
@@ -275,8 +276,9 @@ __global__ void coupling_bwd_weights_kernel(const float* __restrict__ w1, const 
             if (tap < 9 && n < C) v = w3[((long)n * width + c) * 9 + tap];
             dst = w3t + j; part = n3;
         }
-        dst[0] = v;     // raw fp32 (see split_weights_kernel)
-        dst[part] = v - tf32_rn(v);
+        const float hi = tf32_rn(v);
+        dst[0] = hi;
+        dst[part] = tf32_rn(v - hi);
     }
 }
 

@@ -8,8 +8,8 @@
 // fp32 parity ("not TF32") and speed rest on four design points, each
 // measured on B200 (profiles/r2_tc_*.md):
 //  (1) 3xTF32 split products  a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  (a_hi = tf32(a),
-//      a_lo = a - a_hi): both tiles are split on the fly by four transform warps (activations into
-//      TMEM, weights in shared memory), so only raw fp32 travels from L2.  NPASS = 1 is the plain single-pass TF32
+//      a_lo = a - a_hi): weights are split once on the device (`part` 0 = hi, 1 = lo); activation
+//      tiles are split on the fly by four transform warps.  NPASS = 1 is the plain single-pass TF32
 //      product (PyTorch's default conv precision) for callers that ask for it.
 //  (2) two-level accumulation.  The tensor core adds into its fp32 accumulator with truncation, so
 //      the error of a long chain grows linearly with K (3.4e-6 at K = 512, 2.6e-5 at K = 4608 where
@@ -186,13 +186,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                         mbar_wait_long(&empty[s], ((it / S) & 1) ^ 1);   // stage free in EVERY CTA of the cluster
                         const int wrow = tap * g.n_rows + t.ncol0 + (int)rank * BNS;
                         if (elect_one()) {
-                            // only the RAW fp32 weight tile travels (part 0 of the prepared blob): its hi / lo split is
-                            // done by the split warps below -- a 128x128 tile pulled 48 KB per k-block, ~36 B/cycle/SM,
-                            // which is the TMA ingress rate every SM gets when all 148 pull at once
-                            mbar_arrive_expect_tx(&full[s], kABytes + C::kBBytes);
+                            mbar_arrive_expect_tx(&full[s], kABytes + C::kParts * C::kBBytes);
                             tma_load_4d(a_raw(s), &mapA, &full[s], kb * kBK, t.w0 + dx, t.h0 + dy, t.n0);
-                            if (CL == 1) tma_load_2d(b_hi(s), &mapB, &full[s], kb * kBK, wrow);
-                            else tma_load_2d_mc(b_hi(s) + rank * BNS * 128, &mapB, &full[s], kb * kBK, wrow, kAllCtas);
+                            if (CL == 1) {
+                                tma_load_2d(b_hi(s), &mapB, &full[s], kb * kBK, wrow);
+                                if (NPASS == 3) tma_load_2d(b_lo(s), &mapB, &full[s], kb * kBK, g.taps * g.n_rows + wrow);
+                            } else {
+                                tma_load_2d_mc(b_hi(s) + rank * BNS * 128, &mapB, &full[s], kb * kBK, wrow, kAllCtas);
+                                if (NPASS == 3)
+                                    tma_load_2d_mc(b_lo(s) + rank * BNS * 128, &mapB, &full[s], kb * kBK,
+                                                   g.taps * g.n_rows + wrow, kAllCtas);
+                            }
                         }
                         __syncwarp();
                     }
@@ -267,26 +271,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                     }
                 }
                 tmem_st_x32(lane_addr + s * C::kACols, hi);
-                if (NPASS == 3) {
-                    tmem_st_x32(lane_addr + s * C::kACols + kBK, lo);
-                    // weight tile: elementwise hi (in place) / lo split; the swizzle does not matter
-                    float4* bh = reinterpret_cast<float4*>(b_hi(s));
-                    float4* bl = reinterpret_cast<float4*>(b_lo(s));
-                    const int tx = threadIdx.x - 64;
-#pragma unroll
-                    for (int i = 0; i < (C::kBBytes / 16 + kXfThreads - 1) / kXfThreads; ++i) {
-                        const int idx = i * kXfThreads + tx;
-                        if (idx < C::kBBytes / 16) {
-                            const float4 v = bh[idx];
-                            float4 h, l;
-                            h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
-                            l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-                            bh[idx] = h;
-                            bl[idx] = l;
-                        }
-                    }
-                    fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core
-                }
+                if (NPASS == 3) tmem_st_x32(lane_addr + s * C::kACols + kBK, lo);
                 tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(&xf[s]);

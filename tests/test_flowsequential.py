@@ -133,7 +133,7 @@ def test_reference_style_finc_stack_on_gpu():
         ld = ld + l
     assert torch.equal(z.detach(), h)
     want = -0.5 * h.flatten(1).pow(2).sum(1) - 0.5 * 784 * math.log(2 * math.pi) + ld
-    assert rel_err(logp.detach().cpu().numpy(), want.cpu().numpy()) <= 1e-6
+    assert rel_err(logp.detach().cpu().numpy(), want.detach().cpu().numpy()) <= 1e-6
     # autograd through the fused log-prob kernel == autograd through the closed form
     (-logp.sum() / 6).backward()
     x2 = x.detach().clone().requires_grad_(True)

@@ -246,8 +246,13 @@ def test_full_depth_flows_match_the_reference_model(tag):
     while f"{tag}/zs/{n}" in g.files:
         n += 1
     assert len(zs) == n
+    # cfg2 (17 flow steps): latents and log-likelihood <= 1e-5.  cfg3 is 48 steps deep and its key-seeded
+    # parameters grow the latents to rms ~90, so log p ~ -|z|^2 / 2 ~ -1e7 carries TWICE the relative latent
+    # error: latents <= 2e-5 (measured 1e-6 .. 8e-6; PyTorch's own fp32 GPU path: 2e-6 .. 6e-6), log p <= 5e-5
+    # (measured 1.2e-5; PyTorch GPU path 1.0e-5)
+    tol_z, tol_l = (1e-5, 1e-5) if tag == "cfg2" else (2e-5, 5e-5)
     for i, z in enumerate(zs):
-        assert rel_err(z.cpu().numpy(), g[f"{tag}/zs/{i}"]) <= 1e-4, (tag, i, rel_err(z.cpu().numpy(), g[f"{tag}/zs/{i}"]))
-    assert rel_err(logp.cpu().numpy(), g[f"{tag}/logp"]) <= 1e-5
-    assert rel_err(bpd.cpu().numpy(), g[f"{tag}/bpd"]) <= 1e-5
+        assert rel_err(z.cpu().numpy(), g[f"{tag}/zs/{i}"]) <= tol_z, (tag, i, rel_err(z.cpu().numpy(), g[f"{tag}/zs/{i}"]))
+    assert rel_err(logp.cpu().numpy(), g[f"{tag}/logp"]) <= tol_l
+    assert rel_err(bpd.cpu().numpy(), g[f"{tag}/bpd"]) <= tol_l
     assert (x_rec - x).abs().max().item() <= 1 and (x_rec != x).float().mean().item() < 1e-3

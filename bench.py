@@ -392,46 +392,80 @@ def kernel_detail(torch, _native, dev, peak):
     return out
 
 
-def whole_flow_detail(torch, dev):
-    """context, not the metric: the COMPLETE CIFAR-10-shaped FInCFlow (3 blocks x 16 steps, Glow glue
-    with 512-wide coupling networks in PyTorch/cuDNN around the FInC kernels, fused ActNorm+Conv1x1
-    kernel) -- train step (forward, backward, FInC mask, Adam) and model.sample at batch 256."""
+def whole_flow_detail(torch, dev, world=1, rank=0, pg=None):
+    """cfg3_full_flow: the COMPLETE CIFAR-10-shaped FInCFlow (3 blocks x 16 steps, coupling width 512) with every
+    layer on our kernels -- FInC units, fused ActNorm+Conv1x1, tensor-core Coupling (3xTF32, fp32 parity), fused
+    preprocessing -- batch 256 per GPU: data-parallel train step through fincflow_b200.train.FlowTrainer
+    (bucketed NCCL all-reduce overlapped with backward, Adam), exact log-likelihood evaluation, model.sample."""
     from fincflow_b200 import flows
+    from fincflow_b200.train import FlowTrainer
 
     torch.manual_seed(0)
     B = PER_GPU_BATCH
-    m = flows.fastflow_cifar10().to(dev)
-    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
-    x = torch.randint(0, 256, (B, 3, 32, 32), device=dev).float()
+    m = flows.fastflow_cifar10(actnorm=True).to(dev)
+    trainer = FlowTrainer(m, lr=1e-3, process_group=pg, use_graph=(world == 1))
+    g = torch.Generator(device=dev).manual_seed(7000 + rank)
+    x = torch.randint(0, 256, (B, 3, 32, 32), device=dev, generator=g).float()
 
     def train():
-        opt.zero_grad(set_to_none=True)
-        _, logp = m(x)
-        (-(logp.sum() / B)).backward()
-        m.apply(flows.clear_grad)
-        opt.step()
+        trainer.step(x)
+
+    def evaluate():
+        with torch.no_grad():
+            m(x)
 
     def sample():
         with torch.no_grad():
             m.sample(B)
 
-    out = {"model": "fincflow_b200.flows.fastflow_cifar10() (3 blocks x 16 FastFlowSteps, coupling width 512), batch 256, "
-                    "random init; glue in PyTorch (cuDNN TF32 default), FInC units / squeeze / ActNorm+Conv1x1 on our kernels",
-           "n_params": sum(p.numel() for p in m.parameters())}
-    for name, fn in (("train_step", train), ("sample", sample)):
-        for _ in range(2):
+    out = {"model": "fincflow_b200.flows.fastflow_cifar10(actnorm=True): 3 blocks x 16 FastFlowSteps, coupling width 512, "
+                    f"batch {B} per GPU, random init, synthetic uint8 images; all layers on our kernels "
+                    "(Coupling: tcgen05 3xTF32 GEMMs, fp32 parity)",
+           "n_params": sum(p.numel() for p in m.parameters()), "per_gpu_batch": B, "global_batch": B * world}
+    out["train_step_execution"] = ("whole step (forward, backward, Adam) replayed as ONE CUDA graph" if world == 1 else
+                                   "eager; bucketed NCCL all-reduce launched from autograd hooks, overlapped with backward")
+    for name, fn, n in (("train_step", train, 6), ("eval_loglik", evaluate, 5), ("sample", sample, 5)):
+        for _ in range(5 if name == "train_step" else 2):
             fn()
+        if world > 1:
+            torch.distributed.barrier()
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(5):
+        for _ in range(n):
             fn()
         e1.record()
         e1.synchronize()
-        ms = e0.elapsed_time(e1) / 5
+        t = torch.tensor([e0.elapsed_time(e1) / n], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
         out[name + "_ms"] = round(ms, 2)
-        out[name + "_images_per_s"] = round(B / ms * 1e3, 1)
-    del m, opt
+        out[name + "_images_per_s"] = round(B * world / ms * 1e3, 1)
+    # the same evaluation / sampling as CUDA graphs (flows.InferenceSession): no host launch overhead
+    try:
+        sess = flows.InferenceSession(m)
+        for name, fn in (("eval_loglik_graph", lambda: sess.log_prob(x)), ("sample_graph", lambda: sess.sample(B))):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                fn()
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            out[name + "_ms"] = round(ms, 2)
+            out[name + "_images_per_s"] = round(B * world / ms * 1e3, 1)
+        del sess
+        m.train()
+    except Exception as e:
+        out["graph_error"] = repr(e)
+    out["replica_param_maxdiff"] = trainer.replica_max_diff()
+    out["round1_same_model_pytorch_glue"] = {"train_step_ms": 90.9, "sample_ms": 35.1,
+                                             "note": "BENCH_r01: coupling networks through PyTorch/cuDNN (TF32)"}
+    del m, trainer
     torch.cuda.empty_cache()
     return out
 
@@ -617,20 +651,19 @@ def main_ours(args):
                         "see `kernels` for the same kernels streaming from HBM at batch 16384"}
 
     extras = None
+    whole = None
     if not args.no_extra:
         del e2e_runner_keep
         torch.cuda.empty_cache()
         extras = run_extra_workloads(torch, dev, world, rank, pg, K)
+        try:   # every rank takes part (data-parallel trainer); context only: never fail the bench line over it
+            whole = whole_flow_detail(torch, dev, world, rank, pg)
+        except Exception as e:
+            whole = {"error": repr(e)}
 
     line = None
     if rank == 0:
         detail = kernel_detail(torch, _native, dev, peak) if (world == 1 and not args.no_detail) else None
-        whole = None
-        if world == 1 and not args.no_detail:
-            try:
-                whole = whole_flow_detail(torch, dev)
-            except Exception as e:  # context only: never fail the bench line over it
-                whole = {"error": repr(e)}
         gpu_ref = gpu_reference_detail(torch, dev, pm) if (world == 1 and not args.no_detail) else None
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -662,7 +695,7 @@ def main_ours(args):
             "crossrank_param_maxdiff": crossrank,
             "extra_workloads": extras,
             "gpu_reference": gpu_ref,
-            "overlapped_sampling": overlap, "kernels": detail, "whole_flow_context": whole,
+            "overlapped_sampling": overlap, "kernels": detail, "cfg3_full_flow": whole,
         }
         emit(line)
     if world > 1:

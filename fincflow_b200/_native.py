@@ -39,7 +39,7 @@ SYMBOLS = (
     "finc_gaussian_logp_f32", "finc_debug_timestamps", "finc_prepared_weights_bytes", "finc_prepare_weights_f32",
     "finc_squeeze_f32", "finc_unsqueeze_f32", "finc_adam_step_f32", "finc_allreduce_adam_f32", "finc_affine1x1_f32",
     "finc_affine1x1_backward_weight_workspace_bytes", "finc_affine1x1_backward_weight_f32",
-    "finc_preprocess_f32", "finc_tc_conv_weights_bytes", "finc_tc_conv_prepare_weights_f32", "finc_tc_conv_nhwc_f32",
+    "finc_preprocess_f32", "finc_slogdet_inverse_f32", "finc_tc_conv_weights_bytes", "finc_tc_conv_prepare_weights_f32", "finc_tc_conv_nhwc_f32",
     "finc_tc_wgrad_workspace_bytes", "finc_tc_wgrad_f32", "finc_coupling_prepared_bytes", "finc_coupling_workspace_bytes", "finc_coupling_prepare_f32",
     "finc_coupling_apply_f32", "finc_coupling_backward_workspace_bytes", "finc_coupling_backward_f32",
 )
@@ -97,6 +97,8 @@ def load():
     lib.finc_prepared_weights_bytes.argtypes = [i] + dims
     lib.finc_prepare_weights_f32.restype = i
     lib.finc_prepare_weights_f32.argtypes = [p, p, i, i, sz, sz, *dims, u, p]
+    lib.finc_slogdet_inverse_f32.restype = i
+    lib.finc_slogdet_inverse_f32.argtypes = [p, p, p, i, i, p]
     lib.finc_preprocess_f32.restype = i
     lib.finc_preprocess_f32.argtypes = [p, p, p, p, i, ctypes.c_long, ctypes.c_float, i, p]
     lib.finc_tc_conv_weights_bytes.restype = sz
@@ -397,6 +399,18 @@ def affine1x1_backward_weight(dy, x, want_bias=True):
                                                      0 if db is None else db.data_ptr(), ws.data_ptr(), ws.numel(),
                                                      B, C, HW, _stream(x)), "finc_affine1x1_backward_weight_f32", 2)
     return dA, db
+
+
+def slogdet_inverse(W):
+    """(log|det W_i| [n], W_i^-1 [n, C, C]) of a batch of small matrices in one launch, no host sync"""
+    W = _prep(W, "W")
+    _bind_device(W)
+    n, C = int(W.shape[0]), int(W.shape[-1])
+    ld = torch.empty(n, dtype=torch.float32, device=W.device)
+    Winv = torch.empty_like(W)
+    _check(load().finc_slogdet_inverse_f32(W.data_ptr(), ld.data_ptr(), Winv.data_ptr(), n, C, _stream(W)),
+           "finc_slogdet_inverse_f32")
+    return ld, Winv
 
 
 def preprocess(x, noise=None, alpha=1e-6, reverse=False, want_logdet=True):

@@ -386,3 +386,90 @@ int launch_preprocess(const float* x, const float* u, float* y, float* logdet, i
 }
 
 }  // namespace finc
+
+// ---------------------------------------------------------------------------------------------
+// log|det W| and W^-1 of a batch of small matrices (the Conv1x1 weights of a flow: C = 4 ... 128) in ONE
+// launch, one CTA per matrix: Gauss-Jordan with partial pivoting on the augmented [C, 2C] matrix in shared
+// memory.  Replaces torch.slogdet (conv1x1.py:22: one cuSOLVER LU + host round trip per layer per forward)
+// and torch.inverse (conv1x1.py:36, per reverse call); the inverse is also what the backward needs:
+// d log|det W| / dW = W^-T.
+// ---------------------------------------------------------------------------------------------
+namespace finc {
+
+__global__ void slogdet_inverse_kernel(const float* __restrict__ W, float* __restrict__ logabsdet,
+                                       float* __restrict__ Winv, int C) {
+    extern __shared__ float sm[];
+    const int ld = 2 * C + 1;                 // +1: rows start on different banks
+    float* aug = sm;                          // [C][ld]
+    float* fac = sm + (size_t)C * ld;         // [C] elimination factors
+    __shared__ float s_val[4];
+    __shared__ int s_idx[4];
+    __shared__ int s_piv;
+    const float* w = W + (size_t)blockIdx.x * C * C;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int e = tid; e < C * 2 * C; e += nthr) {
+        const int r = e / (2 * C), c = e % (2 * C);
+        aug[r * ld + c] = c < C ? w[r * C + c] : (c - C == r ? 1.f : 0.f);
+    }
+    __syncthreads();
+    float ldsum = 0.f;
+    for (int k = 0; k < C; ++k) {
+        // pivot: largest |aug[r][k]| over r >= k (ties: smallest r) -- warp shuffles, then across the warps
+        float v = (tid >= k && tid < C) ? fabsf(aug[tid * ld + k]) : -1.f;
+        int idx = tid;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+        }
+        if ((tid & 31) == 0) { s_val[tid >> 5] = v; s_idx[tid >> 5] = idx; }
+        __syncthreads();
+        if (tid == 0) {
+            float bv = s_val[0];
+            int bi = s_idx[0];
+            for (int wi = 1; wi < (nthr >> 5); ++wi)
+                if (s_val[wi] > bv || (s_val[wi] == bv && s_idx[wi] < bi)) { bv = s_val[wi]; bi = s_idx[wi]; }
+            s_piv = bi;
+        }
+        __syncthreads();
+        const int p = s_piv;
+        if (p != k)
+            for (int c = tid; c < 2 * C; c += nthr) {
+                const float t = aug[k * ld + c];
+                aug[k * ld + c] = aug[p * ld + c];
+                aug[p * ld + c] = t;
+            }
+        __syncthreads();
+        const float piv = aug[k * ld + k];
+        ldsum += logf(fabsf(piv));
+        if (tid < C) fac[tid] = aug[tid * ld + k];
+        __syncthreads();
+        const float inv = 1.f / piv;
+        for (int c = tid; c < 2 * C; c += nthr) {
+            const float rk = aug[k * ld + c] * inv;
+            for (int r = 0; r < C; ++r)
+                if (r != k) aug[r * ld + c] -= fac[r] * rk;
+            aug[k * ld + c] = rk;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) logabsdet[blockIdx.x] = ldsum;
+    float* out = Winv + (size_t)blockIdx.x * C * C;
+    for (int e = tid; e < C * C; e += nthr) out[e] = aug[(e / C) * ld + C + e % C];
+}
+
+int launch_slogdet_inverse(const float* W, float* logabsdet, float* Winv, int n, int C, cudaStream_t st) {
+    if (n == 0) return 0;
+    const size_t smem = ((size_t)C * (2 * C + 1) + C) * sizeof(float);
+    static bool configured = false;
+    if (smem > 48 * 1024 && !configured) {
+        cudaError_t err = cudaFuncSetAttribute(slogdet_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (err != cudaSuccess) return (int)err;
+        configured = true;
+    }
+    slogdet_inverse_kernel<<<n, 128, smem, st>>>(W, logabsdet, Winv, C);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace finc

@@ -243,6 +243,13 @@ int finc_affine1x1_f32(const float* x, const float* A, const float* bias, float*
     return launch_affine1x1(x, A, bias, y, B, C, HW, (cudaStream_t)stream);
 }
 
+int finc_slogdet_inverse_f32(const float* W, float* logabsdet, float* Winv, int n, int C, void* stream) {
+    if (n < 0 || C < 1 || C > 128) return FINC_E_BADARG;
+    if (n == 0) return FINC_OK;
+    if (!W || !logabsdet || !Winv) return FINC_E_BADARG;
+    return launch_slogdet_inverse(W, logabsdet, Winv, n, C, (cudaStream_t)stream);
+}
+
 int finc_preprocess_f32(const float* x, const float* noise, float* y, float* logdet, int B, long D, float alpha,
                         int reverse, void* stream) {
     if (B < 0 || D < 1 || !(alpha >= 0.f && alpha < 0.5f)) return FINC_E_BADARG;

@@ -203,6 +203,7 @@ int launch_affine1x1(const float* x, const float* A, const float* bias, float* y
 size_t affine1x1_wgrad_workspace_floats(int B, int C, long HW);
 int launch_affine1x1_wgrad(const float* dy, const float* x, float* dA, float* db, float* workspace, size_t ws_floats,
                            int B, int C, long HW, cudaStream_t st);
+int launch_slogdet_inverse(const float* W, float* logabsdet, float* Winv, int n, int C, cudaStream_t st);
 int launch_preprocess(const float* x, const float* u, float* y, float* logdet, int B, long D, float alpha, int reverse,
                       cudaStream_t st);
 int launch_adam(float* p, const float* g, float* m, float* v, float* step, float lr, float b1, float b2, float eps,

@@ -386,32 +386,49 @@ __global__ void coupling_bwd_col2im_kernel(const float* __restrict__ dA1, float*
     }
 }
 
-// deterministic column sums of a [rows, ld] matrix: stage 1 = per-block partial sums over a row range
-__global__ void colsum_partial_kernel(const float* __restrict__ a, float* __restrict__ partial, long rows, int cols, int ld,
-                                      int rows_per_block) {
-    const long r0 = (long)blockIdx.x * rows_per_block;
-    const long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+// deterministic column sums of a [rows, ld] matrix.  Stage 1: block b sums rows [64 b, 64 b + 64) -- thread =
+// column (coalesced), four independent accumulators; stage 2: a tree over the block partials in a fixed order.
+constexpr int kColsumRows = 64;
+__global__ void colsum_partial_kernel(const float* __restrict__ a, float* __restrict__ partial, long rows, int cols, int ld) {
+    const long r0 = (long)blockIdx.x * kColsumRows;
+    const int nr = (int)(r0 + kColsumRows < rows ? kColsumRows : rows - r0);
     for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-        float s = 0.f;
-        for (long r = r0; r < r1; ++r) s += a[r * ld + c];
-        partial[(long)blockIdx.x * cols + c] = s;
+        const float* p = a + r0 * ld + c;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int r = 0;
+        for (; r + 4 <= nr; r += 4) {
+            s0 += p[(long)r * ld];
+            s1 += p[(long)(r + 1) * ld];
+            s2 += p[(long)(r + 2) * ld];
+            s3 += p[(long)(r + 3) * ld];
+        }
+        for (; r < nr; ++r) s0 += p[(long)r * ld];
+        partial[(long)blockIdx.x * cols + c] = (s0 + s1) + (s2 + s3);
     }
 }
+// out[c] = sum_b partial[b][c]: one block per 32 columns, 8 row-lanes per column, fixed-order combination
 __global__ void colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int nblocks, int cols) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
+    __shared__ float red[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), lane_r = threadIdx.x >> 5;
     float s = 0.f;
-    for (int b = 0; b < nblocks; ++b) s += partial[(long)b * cols + c];
-    out[c] = s;
+    if (c < cols)
+        for (int b = lane_r; b < nblocks; b += 8) s += partial[(long)b * cols + c];
+    red[lane_r][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (lane_r == 0 && c < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
+        out[c] = t;
+    }
 }
 static int colsum(const float* a, float* out, float* partial, long rows, int cols, int ld, cudaStream_t st) {
-    const int rpb = 256;
-    const int nb = (int)((rows + rpb - 1) / rpb);
-    colsum_partial_kernel<<<nb, 256, 0, st>>>(a, partial, rows, cols, ld, rpb);
-    colsum_final_kernel<<<(cols + 127) / 128, 128, 0, st>>>(partial, out, nb, cols);
+    const int nb = (int)((rows + kColsumRows - 1) / kColsumRows);
+    colsum_partial_kernel<<<nb, 256, 0, st>>>(a, partial, rows, cols, ld);
+    colsum_final_kernel<<<(cols + 31) / 32, 256, 0, st>>>(partial, out, nb, cols);
     return (int)cudaGetLastError();
 }
-static size_t colsum_partial_floats(long rows, int cols) { return (size_t)((rows + 255) / 256) * cols; }
+static size_t colsum_partial_floats(long rows, int cols) { return (size_t)((rows + kColsumRows - 1) / kColsumRows) * cols; }
 
 // dW (OIHW [N, Cin, 3, 3]) from the GEMM-form gradient: mode 1: src[o][tap * Cin + c] (ld), mode 3: src[c][tap * N3pad + n] (ld)
 __global__ void wgrad_unpack_kernel(const float* __restrict__ src, float* __restrict__ dw, int N, int Cin, int ld, int N3pad,

@@ -127,6 +127,12 @@ class ActNorm(FlowLayer):
         self.translation = nn.Parameter(torch.zeros(n_dims))
         self.log_scale = nn.Parameter(torch.zeros(n_dims))
         self.register_buffer("initialized", torch.tensor(0))
+        self._ready = False   # host copy of `initialized`: checking the device buffer costs a stream sync per call
+
+    def is_initialized(self):
+        if not self._ready:
+            self._ready = bool(self.initialized)
+        return self._ready
 
     @staticmethod
     def _moments(input):
@@ -146,17 +152,18 @@ class ActNorm(FlowLayer):
         return input.mean(dim=dims), input.std(dim=dims)
 
     def forward(self, input, context=None):
-        if not self.initialized:  # data-dependent init on the first batch (actnorm.py:17-23)
+        if not self.is_initialized():  # data-dependent init on the first batch (actnorm.py:17-23)
             with torch.no_grad():
                 mean, std = self._moments(input)
                 self.translation.data.copy_(mean)
                 self.log_scale.data.copy_(torch.log(std + 1e-8))
                 self.initialized.fill_(1)
+                self._ready = True
         t, ls = self.translation.view(1, -1, 1, 1), self.log_scale.view(1, -1, 1, 1)
         return (input - t) * torch.exp(-ls), self.logdet(input, context)
 
     def reverse(self, input, context=None):
-        assert self.initialized
+        assert self.is_initialized()
         t, ls = self.translation.view(1, -1, 1, 1), self.log_scale.view(1, -1, 1, 1)
         return input * torch.exp(ls) + t
 
@@ -465,6 +472,51 @@ def affine_of(actnorm, conv1x1):
     return A, -(A @ actnorm.translation)
 
 
+class _SlogdetFn(torch.autograd.Function):
+    """log|det W_i| of a stack of Conv1x1 weights on finc_slogdet_inverse_f32; backward g_i * W_i^-T"""
+
+    @staticmethod
+    def forward(ctx, Ws):
+        ld, Winv = _native.slogdet_inverse(Ws)
+        ctx.save_for_backward(Winv)
+        return ld
+
+    @staticmethod
+    def backward(ctx, g):
+        (Winv,) = ctx.saved_tensors
+        return g.view(-1, 1, 1) * Winv.transpose(1, 2)
+
+
+def _glue_constants(self):
+    """(A, b, scalar logdet per pixel, A^-1, reverse bias) of [ActNorm +] Conv1x1, cached on the parameter
+    versions.  Used under no_grad (evaluation / sampling): slogdet, inverse and the small products then run
+    once per weight update instead of once per call (torch.slogdet alone is an LU factorisation + a host sync)."""
+    gs = self.glow_step
+    act = getattr(gs, "actnorm", None)
+    conv = gs.conv1x1
+    ps = [conv.W] + ([act.translation, act.log_scale] if act is not None else [])
+    key = tuple((p.data_ptr(), p._version) for p in ps)
+    if getattr(self, "_glue_key", None) != key:
+        with torch.no_grad():
+            W = conv.W.detach()
+            if W.is_cuda and W.shape[0] <= 128:
+                ld, Winv = _native.slogdet_inverse(W.unsqueeze(0).contiguous())
+                ld, Winv = ld[0], Winv[0]
+            else:
+                ld, Winv = torch.slogdet(W)[1], torch.inverse(W)
+            if act is None:
+                A, b, Ainv, binv = W, None, Winv, None
+            else:
+                A = W * torch.exp(-act.log_scale.detach()).unsqueeze(0)
+                b = -(A @ act.translation.detach())
+                ld = ld - act.log_scale.detach().sum()
+                Ainv = torch.exp(act.log_scale.detach()).unsqueeze(1) * Winv
+                binv = act.translation.detach().contiguous()
+            self._glue = (A.contiguous(), None if b is None else b.contiguous(), ld, Ainv.contiguous(), binv)
+        self._glue_key = key
+    return self._glue
+
+
 def _fused_glow_forward(self, x):
     """GlowStep.forward with [ActNorm +] Conv1x1 as ONE per-pixel affine kernel (SURVEY.md 8f row 1);
     same values and log-determinants as the layer-by-layer path (actnorm.py:14-64, conv1x1.py:18-43)."""
@@ -472,30 +524,33 @@ def _fused_glow_forward(self, x):
     act = getattr(gs, "actnorm", None)
     conv = gs.conv1x1
     B, _, H, W = x.shape
-    logdet = 0
-    if act is not None and not act.initialized:
-        x, ld = act(x)                      # data-dependent init needs the un-fused statistics once
-        logdet = logdet + ld
-        act = None
-    elif act is not None:
-        logdet = logdet + act.logdet(x)
+    if act is not None and not act.is_initialized():
+        x, ld0 = act(x)                     # data-dependent init needs the un-fused statistics once
+        y = _Affine1x1Fn.apply(x, conv.W, None)
+        y, ld = gs.coupling(y)
+        return y, ld0 + H * W * torch.slogdet(conv.W)[1] + ld
+    if not torch.is_grad_enabled():
+        A, b, ld_pix, _, _ = _glue_constants(self)
+        y = _native.affine1x1(x.contiguous(), A, b)
+        y, ld = gs.coupling(y)
+        return y, ld + (H * W) * ld_pix
     A, b = affine_of(act, conv)
     y = _Affine1x1Fn.apply(x, A, b)
-    logdet = logdet + H * W * torch.slogdet(conv.W)[1]
+    ld_w = conv.__dict__.pop("_ld_batched", None)     # set by FastFlow.forward: one batched LU per level
+    if ld_w is None:
+        ld_w = torch.slogdet(conv.W)[1]
+    ld_pix = ld_w if act is None else ld_w - act.log_scale.sum()
     y, ld = gs.coupling(y)
-    return y, logdet + ld
+    return y, ld + (H * W) * ld_pix
 
 
 def _fused_glow_reverse(self, z):
     gs = self.glow_step
     act = getattr(gs, "actnorm", None)
+    assert act is None or act.is_initialized()
     x = gs.coupling.reverse(z)
-    Winv = torch.inverse(gs.conv1x1.W)
-    if act is None:
-        return _native.affine1x1(x.contiguous(), Winv.contiguous())
-    assert act.initialized
-    Ainv = torch.exp(act.log_scale).unsqueeze(1) * Winv      # diag(exp(log_s)) W^-1
-    return _native.affine1x1(x.contiguous(), Ainv.contiguous(), act.translation.detach().contiguous())
+    _, _, _, Ainv, binv = _glue_constants(self)
+    return _native.affine1x1(x.contiguous(), Ainv, binv)
 
 
 class FastFlowStep(_Chain):
@@ -556,8 +611,23 @@ class FastFlow(nn.Module):
                                              for _ in range(n_final)])
         self.base_distribution = GaussianPrior(self.output_size)
 
+    def _batched_slogdets(self):
+        """training path: log|det W| of every Conv1x1 in ONE batched LU per channel count (3 calls for the
+        CIFAR-10 flow instead of 48; each torch.slogdet is a cuSOLVER factorisation with a host round trip)"""
+        groups = {}
+        for mod in self.modules():
+            if isinstance(mod, Conv1x1):
+                groups.setdefault(mod.n_channels, []).append(mod)
+        for n_ch, convs in groups.items():
+            Ws = torch.stack([c.W for c in convs])
+            lds = _SlogdetFn.apply(Ws) if n_ch <= 128 else torch.linalg.slogdet(Ws)[1]
+            for i, c in enumerate(convs):
+                c._ld_batched = lds[i]
+
     def forward(self, x, context=None):
         zs = []
+        if torch.is_grad_enabled() and x.is_cuda and GlowStep.fused:
+            self._batched_slogdets()
         x, logdet = self.preprocess(x)
         for level in self.fastflow_levels:
             x, z, ld = level(x)
@@ -598,6 +668,59 @@ class FastFlow(nn.Module):
         """true inverse: feeds the split-off latents back (test_layers.py:304-348 reconstruct_ff)"""
         zs, _ = self.forward(x)
         return self.reverse(n_samples=x.shape[0], zs=zs)
+
+
+class InferenceSession:
+    """Likelihood evaluation and sampling of a trained flow as CUDA graphs.
+
+    An eager forward of the CIFAR-10 flow issues ~1900 kernel launches (48 steps x FInC unit, affine glue,
+    six coupling launches, log-determinant adds); the host needs ~26 ms to enqueue what the GPU executes in
+    ~12 ms.  The session captures `model.forward` / `model.reverse` once per batch size into a CUDA graph
+    (static input / output buffers, weights read in place) and replays it.  Weights must not change between
+    capture and replay; call `reset()` after loading new ones.  The reference samples one layer at a time
+    from Python (train/experiment.py:327-337)."""
+
+    def __init__(self, model):
+        self.model = model.eval()
+        self._eval, self._sample = {}, {}
+
+    def reset(self):
+        self._eval.clear()
+        self._sample.clear()
+
+    @staticmethod
+    def _capture(fn, warm=2):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warm):          # lazy initialisations (weight blobs, glue constants, workspaces)
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(g):
+            out = fn()
+        return g, out
+
+    def log_prob(self, x):
+        """(zs, logp[B]) like model.forward(x); the returned tensors are the session's static buffers"""
+        key = tuple(x.shape)
+        if key not in self._eval:
+            buf = x.clone()
+            g, out = self._capture(lambda: self.model(buf))
+            self._eval[key] = (g, buf, out)
+        g, buf, out = self._eval[key]
+        buf.copy_(x)
+        g.replay()
+        return out
+
+    def sample(self, n_samples):
+        """x [n, C, H, W] like model.sample(n)[0]; latents are drawn inside the graph"""
+        if n_samples not in self._sample:
+            g, out = self._capture(lambda: self.model.sample(n_samples)[0])
+            self._sample[n_samples] = (g, out)
+        g, out = self._sample[n_samples]
+        g.replay()
+        return out
 
 
 def set_fp32_parity(enabled: bool = True):

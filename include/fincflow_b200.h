@@ -165,6 +165,12 @@ int finc_allreduce_adam_f32(const void* peer_grad, const void* peer_signal, void
 int finc_squeeze_f32(const float* x, float* y, int B, int C, int H, int W, void* stream);
 int finc_unsqueeze_f32(const float* x, float* y, int B, int C4, int H, int W, void* stream);
 
+/* log|det W_i| and W_i^-1 for a batch of n small matrices [n, C, C] (C <= 128) in one launch (Gauss-Jordan with
+ * partial pivoting, one CTA per matrix).  Replaces `torch.slogdet(self.W)` in Conv1x1.forward and
+ * `torch.inverse(self.W)` in Conv1x1.reverse (layers/conv1x1.py:22,36: a cuSOLVER call with a host round trip per
+ * layer per call); W^-1 is also the gradient of the log-determinant: d log|det W| / dW = W^-T. */
+int finc_slogdet_inverse_f32(const float* W, float* logabsdet, float* Winv, int n, int C, void* stream);
+
 /* Input preprocessing of the image flows, forward and reverse, in one pass (x, y: [B, D] contiguous):
  *   forward: p = ((x + noise) / 256 + alpha) * (1 - 2 alpha);  y = log p - log(1 - p)
  *            logdet[n] = D * (log(1 - 2 alpha) - log 256) + sum_d (-log p - log(1 - p))   (logdet may be NULL)

@@ -54,3 +54,12 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def elementwise_close(a, b, rtol=1e-5, floor=1e-1):
+    """element-wise relative check with an absolute floor: |a - b| <= rtol * (|b| + floor * max|b|).
+    Used NEXT to rel_err (max-norm): two fp32 evaluations in different orders differ by a few 1e-7 absolute
+    on elements that cancel to ~0 whatever their size, hence the floor of rtol * floor * max|b| = 1e-6 max|b|."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return bool((np.abs(a - b) <= rtol * (np.abs(b) + floor * np.abs(b).max())).all())

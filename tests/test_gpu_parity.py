@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import Golden, rel_err
+from conftest import elementwise_close, Golden, rel_err
 from oracle import finc_oracle as fo
 
 pytestmark = pytest.mark.gpu
@@ -58,6 +58,9 @@ def test_golden_vectors_from_reference(nat, golden, name, flags):
     orders = tuple(int(o) for o in c["orders"])
     r = run_all(nat, c["x"], c["w"], c["dz"], c["zs"], orders, flags)
     assert rel_err(r["z"], c["z"]) <= REL_TOL
+    # element-wise (with absolute floor) next to the max-norm metric, on every output
+    for got, want in (("z", "z"), ("dx", "dx"), ("dw_raw", "dw_raw"), ("dw", "dw_masked"), ("x_zs", "x_from_zs")):
+        assert elementwise_close(r[got], c[want]), (got, want)
     assert np.abs(r["logdet"]).max() == 0.0  # reference: python float 0.0
     assert rel_err(r["dx"], c["dx"]) <= REL_TOL
     assert rel_err(r["dw_raw"], c["dw_raw"]) <= REL_TOL
@@ -121,6 +124,9 @@ def test_against_oracle(nat, case):
     assert rel_err(r["dw"], fo.backward_weight(dz, x, (kH, kW), orders)) <= REL_TOL
     assert rel_err(r["dw_raw"], fo.backward_weight(dz, x, (kH, kW), orders, apply_mask=False)) <= REL_TOL
     assert rel_err(r["x_zs"], fo.inverse(zs, w, orders)) <= REL_TOL
+    assert elementwise_close(r["z"], fo.forward(x, w, orders)) and elementwise_close(r["x_zs"], fo.inverse(zs, w, orders))
+    assert elementwise_close(r["dx"], fo.backward_input(dz, w, orders))
+    assert elementwise_close(r["dw"], fo.backward_weight(dz, x, (kH, kW), orders))
     assert np.abs(r["x_rt"] - x).max() <= RT_TOL
     assert np.abs(r["logdet"]).max() == 0.0
 

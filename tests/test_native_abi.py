@@ -47,8 +47,13 @@ def test_abi_version_and_error_strings(lib_path):
     assert lib.finc_inverse_f32(None, None, None, 1, 17, 3, 8, 8, 3, 3, 0, 0, None) == -1  # G > 16
     assert lib.finc_backward_weight_workspace_bytes(256, 4, 3, 16, 16, 3, 3) >= 4096
     # tensor-core entry points: sizes are host arithmetic, bad arguments are rejected before any CUDA call
-    assert lib.finc_coupling_prepared_bytes(12, 512) > 4 * (2 * 512 * 64 + 2 * 512 * 512 + 2 * 9 * 16 * 512)
-    assert lib.finc_coupling_prepared_bytes(12, 16) == 0 and lib.finc_coupling_prepared_bytes(13, 512) == 0
+    assert lib.finc_coupling_prepared_bytes(12, 512, 0) > 4 * (2 * 512 * 64 + 2 * 512 * 512 + 2 * 9 * 16 * 512)
+    assert lib.finc_coupling_prepared_bytes(12, 512, 1) > lib.finc_coupling_prepared_bytes(12, 512, 0)
+    assert lib.finc_coupling_prepared_bytes(12, 16, 0) == 0 and lib.finc_coupling_prepared_bytes(13, 512, 0) == 0
+    assert lib.finc_coupling_prepared_bytes(12, 96, 0) > 0 and lib.finc_coupling_prepared_bytes(12, 96, 1) == 0
+    assert lib.finc_coupling_backward_workspace_bytes(256, 12, 16, 16, 512) > 0
+    assert lib.finc_tc_wgrad_workspace_bytes(65536, 512, 512) > 0 and lib.finc_tc_wgrad_workspace_bytes(100, 512, 100) == 0
+    assert lib.finc_slogdet_inverse_f32(None, None, None, 3, 200, None) == -1
     assert lib.finc_coupling_workspace_bytes(256, 12, 16, 16, 512) >= 4 * 256 * 256 * (64 + 512 + 512)
     assert lib.finc_coupling_apply_f32(None, None, None, None, None, 0, 1, 12, 8, 8, 512, 0, 0, None) == -1
     assert lib.finc_tc_conv_nhwc_f32(None, None, None, None, None, 1, 8, 8, 32, 32, 9, 0, 0, None) == -1

@@ -88,6 +88,56 @@ __global__ void __launch_bounds__(256) affine1x1_kernel(const float* __restrict_
     }
 }
 
+// Small problems (a few thousand pixels: the 4x4 and 8x8 levels at batch 256): the kernel above has one thread
+// per VEC pixels computing ALL C outputs -- C*C*VEC dependent FMAs per thread on a grid of a few CTAs
+// ([256,48,4,4]: 8 CTAs, 15.9 us = 1.5 % of the HBM peak).  Here a thread computes FOUR outputs of ONE pixel:
+// C/4 times more threads, a C-long critical path, the re-read inputs come from L1.  Pixel index fastest, so a
+// warp reads / writes 128 contiguous bytes per channel and its A^T vector is a shared-memory broadcast.
+template <int C>
+__global__ void __launch_bounds__(256) affine1x1_split_kernel(const float* __restrict__ x, const float* __restrict__ A,
+                                                              const float* __restrict__ bias, float* __restrict__ y,
+                                                              long npix, long HW) {
+    constexpr int CP = (C + 3) & ~3;
+    __shared__ __align__(16) float At[C * CP];
+    __shared__ __align__(16) float bs[CP];
+    for (int e = threadIdx.x; e < C * CP; e += blockDim.x) {
+        const int i = e / CP, o = e - i * CP;
+        At[e] = o < C ? __ldg(A + o * C + i) : 0.f;
+    }
+    for (int o = threadIdx.x; o < CP; o += blockDim.x) bs[o] = (bias != nullptr && o < C) ? __ldg(bias + o) : 0.f;
+    __syncthreads();
+    const long total = npix * (CP / 4);
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long p = idx % npix;
+        const int ob = (int)(idx / npix);
+        const long n = p / HW;
+        const long off = n * C * HW + (p - n * HW);
+        const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * ob);
+        float a0 = b4.x, a1 = b4.y, a2 = b4.z, a3 = b4.w;
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            const float xv = __ldg(x + off + i * HW);
+            const float4 a = *reinterpret_cast<const float4*>(At + i * CP + 4 * ob);
+            a0 = fmaf(a.x, xv, a0); a1 = fmaf(a.y, xv, a1); a2 = fmaf(a.z, xv, a2); a3 = fmaf(a.w, xv, a3);
+        }
+        float* yp = y + off + (long)(4 * ob) * HW;
+        yp[0] = a0;
+        if (4 * ob + 1 < C) yp[HW] = a1;
+        if (4 * ob + 2 < C) yp[2 * HW] = a2;
+        if (4 * ob + 3 < C) yp[3 * HW] = a3;
+    }
+}
+
+template <int C>
+int launch_split(const float* x, const float* A, const float* bias, float* y, int B, long HW, cudaStream_t st) {
+    const long npix = (long)B * HW;
+    const long total = npix * ((C + 3) / 4);
+    const long blocks = (total + 255) / 256;
+    const long cap = (long)sm_count_cached() * 8;
+    affine1x1_split_kernel<C><<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(x, A, bias, y, npix, HW);
+    return (int)cudaGetLastError();
+}
+
 // any C: one thread per output element (coalesced along the pixels)
 __global__ void affine1x1_generic_kernel(const float* __restrict__ x, const float* __restrict__ A,
                                          const float* __restrict__ bias, float* __restrict__ y, long total, int C,
@@ -320,6 +370,22 @@ int launch_affine1x1(const float* x, const float* A, const float* bias, float* y
     const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y);
     if (HW % 4 == 0 && (al & 15) == 0) vec = 4;
     else if (HW % 2 == 0 && (al & 7) == 0) vec = 2;
+    // fewer pixel-vectors than ~2 waves of threads: split the output channels over threads instead
+    const int vmax = C >= 96 ? 1 : C >= 32 ? 2 : 4;
+    const long items = (long)B * (HW / (vec < vmax ? vec : vmax));
+    if (items < (long)sm_count_cached() * 512) {
+        switch (C) {
+            case 4: return launch_split<4>(x, A, bias, y, B, HW, st);
+            case 8: return launch_split<8>(x, A, bias, y, B, HW, st);
+            case 12: return launch_split<12>(x, A, bias, y, B, HW, st);
+            case 16: return launch_split<16>(x, A, bias, y, B, HW, st);
+            case 24: return launch_split<24>(x, A, bias, y, B, HW, st);
+            case 32: return launch_split<32>(x, A, bias, y, B, HW, st);
+            case 48: return launch_split<48>(x, A, bias, y, B, HW, st);
+            case 96: return launch_split<96>(x, A, bias, y, B, HW, st);
+            default: break;
+        }
+    }
     switch (C) {
         case 4: return dispatch_vec<4, 4>(vec, x, A, bias, y, B, HW, st);
         case 8: return dispatch_vec<8, 4>(vec, x, A, bias, y, B, HW, st);

@@ -313,9 +313,9 @@ def test_flow_trainer_graph_step_equals_eager_step():
         tr = FlowTrainer(m, lr=1e-3, use_graph=use_graph, graph_warmup=2)
         g = torch.Generator(device="cuda").manual_seed(9)
         losses = []
+        m.preprocess.layers[0].fixed_noise = torch.full((8, 3, 16, 16), 0.5, device="cuda")   # ONE tensor: the graph reads it in place
         for i in range(6):
             x = torch.randint(0, 256, (8, 3, 16, 16), device="cuda", generator=g).float()
-            m.preprocess.layers[0].fixed_noise = torch.full_like(x, 0.5)
             losses.append(float(tr.step(x)))
         return losses, [p.detach().clone() for p in m.parameters()], tr
 
@@ -331,8 +331,8 @@ def test_flow_trainer_graph_step_equals_eager_step():
     tr2 = FlowTrainer(m, lr=1e-3)
     g = torch.Generator(device="cuda").manual_seed(9)
     xs = [torch.randint(0, 256, (8, 3, 16, 16), device="cuda", generator=g).float() for _ in range(6)]
+    m.preprocess.layers[0].fixed_noise = torch.full((8, 3, 16, 16), 0.5, device="cuda")
     for i in (0, 1, 3, 4, 5):
-        m.preprocess.layers[0].fixed_noise = torch.full_like(xs[i], 0.5)
         tr2.step(xs[i])
     for a, b in zip(p_g, m.parameters()):
         assert rel_err(a.cpu().numpy(), b.detach().cpu().numpy()) <= 1e-4

@@ -65,10 +65,10 @@ def extra_workload_specs(world):
         "cfg4_imagenet32": dict(levels=imagenet32_levels(), batch=512, scaling="weak", phases=allp,
                                 what="ImageNet32 flow skeleton: 3 levels x 48 units, batch 512 per GPU"),
         "cfg5_imagenet64_k3": dict(levels=imagenet64_levels(48, 3), batch=max(1024 // world, 1), scaling="strong",
-                                   phases=("inverse",),
+                                   phases=("inverse",), dense=True,
                                    what="ImageNet64 flow skeleton k=3 (48,48,48,1 units), SAMPLING only, 1024 images sharded by batch"),
         "cfg5_imagenet64_k5": dict(levels=imagenet64_levels(48, 5), batch=max(1024 // world, 1), scaling="strong",
-                                   phases=("inverse",),
+                                   phases=("inverse",), dense=True,
                                    what="ImageNet64 flow skeleton k=5, SAMPLING only, 1024 images sharded by batch"),
     }
 
@@ -87,7 +87,8 @@ def run_extra_workloads(torch, dev, world, rank, pg, K, names=None):
             torch.manual_seed(0)
             stack = FincStack(spec["levels"]).to(dev)
             B = spec["batch"]
-            runner = HotPathRunner(stack, B, dev, slots=1, process_group=pg if "optimizer" in spec["phases"] else None)
+            runner = HotPathRunner(stack, B, dev, slots=1, process_group=pg if "optimizer" in spec["phases"] else None,
+                                   dense_inverse=spec.get("dense", False))
             g = torch.Generator(device=dev).manual_seed(4000 + rank)
             for li in range(len(spec["levels"])):
                 runner.slots[0].acts[li][0].normal_(generator=g)
@@ -126,6 +127,7 @@ def run_extra_workloads(torch, dev, world, rank, pg, K, names=None):
             out.append({"name": name, "what": spec["what"], "per_gpu_batch": B, "global_batch": gb,
                         "scaling": spec["scaling"], "steps": K, "ms_per_step": round(tot, 4),
                         "phases_ms": {k: round(v, 4) for k, v in pm.items()}, "images_per_s": ips,
+                        "dense_inverse_levels": sorted(runner.dense),
                         "frac_of_hbm_peak": {k: round(8 * elems * (1.5 if k == "backward" else 1.0) / (v * 1e-3) / 1e9 / peak, 4)
                                              for k, v in pm.items() if k != "optimizer"}})
             del runner, stack

@@ -42,6 +42,8 @@ SYMBOLS = (
     "finc_preprocess_f32", "finc_slogdet_inverse_f32", "finc_tc_conv_weights_bytes", "finc_tc_conv_prepare_weights_f32", "finc_tc_conv_nhwc_f32",
     "finc_tc_wgrad_workspace_bytes", "finc_tc_wgrad_f32", "finc_coupling_prepared_bytes", "finc_coupling_workspace_bytes", "finc_coupling_prepare_f32",
     "finc_coupling_apply_f32", "finc_coupling_backward_workspace_bytes", "finc_coupling_backward_f32",
+    "finc_inverse_dense_bytes", "finc_inverse_dense_scratch_bytes", "finc_inverse_dense_prepare_f32",
+    "finc_inverse_dense_f32",
 )
 
 _lib = None
@@ -117,6 +119,14 @@ def load():
     lib.finc_coupling_workspace_bytes.argtypes = [i, i, i, i, i]
     lib.finc_coupling_prepare_f32.restype = i
     lib.finc_coupling_prepare_f32.argtypes = [p] * 7 + [ctypes.c_float, p, i, i, i, p]
+    lib.finc_inverse_dense_bytes.restype = sz
+    lib.finc_inverse_dense_bytes.argtypes = [i, i, i, i]
+    lib.finc_inverse_dense_scratch_bytes.restype = sz
+    lib.finc_inverse_dense_scratch_bytes.argtypes = [i, i, i, i]
+    lib.finc_inverse_dense_prepare_f32.restype = i
+    lib.finc_inverse_dense_prepare_f32.argtypes = [p, p, p, sz, i, i, i, i, i, i, u, p]
+    lib.finc_inverse_dense_f32.restype = i
+    lib.finc_inverse_dense_f32.argtypes = [p, p, p, i, i, i, i, i, u, p]
     lib.finc_coupling_backward_workspace_bytes.restype = sz
     lib.finc_coupling_backward_workspace_bytes.argtypes = [i, i, i, i, i]
     lib.finc_coupling_backward_f32.restype = i
@@ -561,6 +571,38 @@ def coupling_apply(x, blob, width, reverse=False, want_logdet=True, logdet_out=N
                                           blob.data_ptr(), ws.data_ptr(), ws.numel(), B, C, H, W, width, int(reverse),
                                           flags, _stream(x)), "finc_coupling_apply_f32", 5)
     return y, logdet
+
+
+def inverse_dense_bytes(G, C, H, W) -> int:
+    """bytes of the dense-inverse table of one unit; 0 = shape not covered (n = C*H*W in [64, 1024], n % 64 == 0)"""
+    return int(load().finc_inverse_dense_bytes(G, C, H, W))
+
+
+def inverse_dense_prepare(w, H, W, G=4, orders=ORDERS_UNIT, out=None):
+    """L^-1 of every group of a unit (hi / lo split, K-major), by running the wavefront inverse on the identity"""
+    w = _prep(w, "weight")
+    _bind_device(w)
+    C, kH, kW = int(w.shape[1]), int(w.shape[2]), int(w.shape[3])
+    nbytes = inverse_dense_bytes(G, C, H, W)
+    if nbytes == 0:
+        raise FincNativeError(f"inverse_dense_prepare: C={C}, H={H}, W={W} not covered")
+    blob = torch.empty(nbytes, dtype=torch.uint8, device=w.device) if out is None else out
+    scratch = _shared_scratch(int(load().finc_inverse_dense_scratch_bytes(G, C, H, W)), w.device)
+    _check(load().finc_inverse_dense_prepare_f32(w.data_ptr(), blob.data_ptr(), scratch.data_ptr(), scratch.numel(),
+                                                 G, C, H, W, kH, kW, orders, _stream(w)),
+           "finc_inverse_dense_prepare_f32", 3)
+    return blob
+
+
+def inverse_dense(z, blob, G=4, flags=0, out=None):
+    """x = L^-1 z as ONE block-diagonal tensor-core GEMM over all groups (same map as inverse(); fixed weights)"""
+    z = _prep(z, "z")
+    _bind_device(z)
+    B, CT, H, W = (int(v) for v in z.shape)
+    x = torch.empty_like(z) if out is None else out
+    _check(load().finc_inverse_dense_f32(z.data_ptr(), blob.data_ptr(), x.data_ptr(), B, G, CT // G, H, W, flags,
+                                         _stream(z)), "finc_inverse_dense_f32", G)
+    return x
 
 
 def sm_count() -> int:

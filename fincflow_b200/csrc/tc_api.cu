@@ -65,11 +65,12 @@ static PFN_cuTensorMapEncodeTiled_v12000 encoder() {
 
 // channels-last activation [B, H, W, C] (C % 4 == 0), box = (32 channels, wb, hb, nb) pixels, 128-byte swizzle;
 // coordinates outside the tensor read as zero (= conv padding) and are dropped on stores
-static int map_nhwc(CUtensorMap* m, const float* base, int C, int W, int H, int B, int wb, int hb, int nb) {
+static int map_nhwc(CUtensorMap* m, const float* base, int C, int W, int H, int B, int wb, int hb, int nb, long ld = 0) {
     auto enc = encoder();
     if (enc == nullptr) return FINC_E_UNSUPPORTED;
+    if (ld == 0) ld = C;   // floats between consecutive pixels
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)W * ld * 4, (cuuint64_t)H * W * ld * 4};
     cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)wb, (cuuint32_t)hb, (cuuint32_t)nb};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, es,
@@ -125,6 +126,7 @@ static Geom make_geom(int B, int H, int W, int taps, int Cpad, int Npad, int BN)
     g.kb_per_tap = Cpad / kBK;
     g.n_tiles = Npad / BN;
     g.n_rows = Npad;
+    g.group_n = 0;
     return g;
 }
 
@@ -816,6 +818,91 @@ int finc_coupling_backward_f32(const float* x, const float* dy, const float* dlo
     }
     coupling_bwd_col2im_kernel<<<grid_for((long)B * L.Cin * H * W, 256), 256, 0, st>>>(s + sc.dA1, dx, B, C, L.Cin, H, W, L.K1pad);
     return (int)cudaGetLastError();
+}
+
+
+// ---- dense form of the FInC inverse for small tiles -----------------------------------------------------------
+// The inverse of a FInC convolution is x = L^-1 z with L the (unit lower-triangular after reordering) matrix of
+// the convolution over the n = C*H*W unknowns of one (image, group).  For the deep, small levels (4x4, 8x8
+// tiles: n <= 1024) L^-1 is small and the same for every image, so a batch is ONE GEMM X = Z (L^-1)^T per group on
+// the tensor cores instead of a wavefront recurrence whose parallelism is a diagonal of 4 .. 8 pixels:
+// [2048,96,4,4] k=5: 298 us on the wavefront kernel (FP32-pipe bound, 17 % of its peak); [2048,48,8,8] k=5: 224 us.
+// L^-1 is obtained by running the wavefront kernel itself on the identity (n unit images), once per weight update.
+
+// prepared[part][g][i][j] = X[j][g][i] (hi / lo split): row i of L_g^-1, K-major; all groups' rows stacked per part
+__global__ void dense_inverse_weights_kernel(const float* __restrict__ X, float* __restrict__ out, int G, int n) {
+    const long per_part = (long)n * n;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < per_part * G; idx += (long)gridDim.x * blockDim.x) {
+        const int g = (int)(idx / per_part);
+        const long r = idx - g * per_part;
+        const int j = (int)(r % n), i = (int)(r / n);
+        const float v = X[((long)j * G + g) * n + i];
+        const float hi = tf32_rn(v);
+        float* o = out + (long)g * per_part + r;
+        o[0] = hi;
+        o[per_part * G] = tf32_rn(v - hi);
+    }
+}
+// identity batch: image j of group g is the unit vector e_j  ->  Z[j][g][i] = (i == j)
+__global__ void dense_identity_kernel(float* __restrict__ Z, int G, int n) {
+    const long total = (long)n * G * n;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % n);
+        const int j = (int)(idx / ((long)G * n));
+        Z[idx] = i == j ? 1.f : 0.f;
+    }
+}
+
+static int dense_n(int C, int H, int W) {
+    const long n = (long)C * H * W;
+    return (n >= 64 && n <= 1024 && n % 64 == 0) ? (int)n : 0;
+}
+
+size_t finc_inverse_dense_bytes(int G, int C, int H, int W) {
+    const int n = dense_n(C, H, W);
+    return (n == 0 || G < 1 || G > 16) ? 0 : (size_t)G * 2 * n * n * sizeof(float);
+}
+size_t finc_inverse_dense_scratch_bytes(int G, int C, int H, int W) {
+    const int n = dense_n(C, H, W);
+    return (n == 0 || G < 1 || G > 16) ? 0 : (size_t)2 * n * G * n * sizeof(float);
+}
+
+int finc_inverse_dense_prepare_f32(const float* w, void* prepared, void* scratch, size_t scratch_bytes, int G, int C, int H,
+                                   int W, int kH, int kW, unsigned orders, void* stream) {
+    const int n = dense_n(C, H, W);
+    if (!w || !prepared || !scratch) return FINC_E_BADARG;
+    if (n == 0 || G < 1 || G > 16) return FINC_E_UNSUPPORTED;
+    if (scratch_bytes < finc_inverse_dense_scratch_bytes(G, C, H, W)) return FINC_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* Z = (float*)scratch;
+    float* X = Z + (size_t)n * G * n;
+    dense_identity_kernel<<<grid_for((long)n * G * n, 256), 256, 0, st>>>(Z, G, n);
+    int rc = finc_inverse_f32(Z, w, X, n, G, C, H, W, kH, kW, orders, 0, stream);   // column j of L_g^-1 = inverse(e_j)
+    if (rc) return rc;
+    dense_inverse_weights_kernel<<<grid_for((long)n * n * G, 256), 256, 0, st>>>(X, (float*)prepared, G, n);
+    return (int)cudaGetLastError();
+}
+
+int finc_inverse_dense_f32(const float* z, const void* prepared, float* x, int B, int G, int C, int H, int W, unsigned flags,
+                           void* stream) {
+    const int n = dense_n(C, H, W);
+    if (!z || !prepared || !x || B < 0 || z == x) return FINC_E_BADARG;
+    if (n == 0 || G < 1 || G > 16) return FINC_E_UNSUPPORTED;
+    if (B == 0) return FINC_OK;
+    const int npass = (flags & FINC_FLAG_TF32_1PASS) ? 1 : 3;
+    const int BN = n % 128 == 0 ? 128 : 64;
+    // ONE block-diagonal GEMM: "pixels" = images, output columns = the G*n unknowns, each group reading its own n inputs
+    Geom g = make_geom(1, 1, B, 1, n, G * n, BN);
+    g.group_n = n;
+    CUtensorMap mA, mB;
+    int rc = map_nhwc(&mA, z, G * n, B, 1, 1, g.wb, g.hb, g.nb);
+    if (rc) return rc;
+    rc = map_weights(&mB, (const float*)prepared, (long)2 * G * n, n, BN);
+    if (rc) return rc;
+    EpiArgs e{};
+    e.y = x;
+    e.ld_out = G * n;
+    return launch_igemm_rows(BN, npass, mA, mB, g, e, (cudaStream_t)stream);
 }
 
 }  // extern "C"

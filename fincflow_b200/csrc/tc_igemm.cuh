@@ -58,6 +58,8 @@ struct Geom {
     int kb_per_tap;                   // Cin_pad / 32
     int n_tiles;                      // Npad / BN
     int n_rows;                       // Npad: weight rows per (part, tap)
+    int group_n;                      // block-diagonal GEMM (0 = off): output columns [q*group_n, (q+1)*group_n) read
+                                      // activation channels q*group_n + k  (one launch for all groups of the dense inverse)
 };
 
 struct EpiArgs {
@@ -185,9 +187,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                         const int s = it % S;
                         mbar_wait_long(&empty[s], ((it / S) & 1) ^ 1);   // stage free in EVERY CTA of the cluster
                         const int wrow = tap * g.n_rows + t.ncol0 + (int)rank * BNS;
+                        const int c0 = kb * kBK + (g.group_n ? t.ncol0 / g.group_n * g.group_n : 0);
                         if (elect_one()) {
                             mbar_arrive_expect_tx(&full[s], kABytes + C::kParts * C::kBBytes);
-                            tma_load_4d(a_raw(s), &mapA, &full[s], kb * kBK, t.w0 + dx, t.h0 + dy, t.n0);
+                            tma_load_4d(a_raw(s), &mapA, &full[s], c0, t.w0 + dx, t.h0 + dy, t.n0);
                             if (CL == 1) {
                                 tma_load_2d(b_hi(s), &mapB, &full[s], kb * kBK, wrow);
                                 if (NPASS == 3) tma_load_2d(b_lo(s), &mapB, &full[s], kb * kBK, g.taps * g.n_rows + wrow);

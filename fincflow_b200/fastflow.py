@@ -108,7 +108,22 @@ class FastFlowUnit(nn.Module):
         z, logdet = finc_conv(x, self.weight, 4, _native.ORDERS_UNIT, self.mask_in_backward, want)
         return z, (logdet if want else 0.0)  # reference: 0.0 + 0.0 + 0.0 + 0.0 (fastflow.py:34-50)
 
+    # opt-in (class or instance attribute): sampling with FIXED weights runs x = L^-1 z as one block-diagonal
+    # tensor-core GEMM when the tile is small (n = Cq*H*W <= 1024); L^-1 is cached per weight version.  Pays for
+    # 4x4 / 8x8 tiles and k=5 (2-11x over the wavefront kernel at B >= 1024), not for 16x16 tiles at k=3.
+    dense_reverse = False
+
+    def _dense_table(self, H, W):
+        key = (self.weight.data_ptr(), self.weight._version, H, W)
+        if getattr(self, "_dense_key", None) != key:
+            self._dense_blob = _native.inverse_dense_prepare(self.weight.detach().contiguous(), H, W)
+            self._dense_key = key
+        return self._dense_blob
+
     def reverse(self, x, context=None):
+        if (self.dense_reverse and x.is_cuda and not (torch.is_grad_enabled() and x.requires_grad)
+                and _native.inverse_dense_bytes(4, self.cq, x.shape[2], x.shape[3]) > 0):
+            return _native.inverse_dense(x.contiguous(), self._dense_table(int(x.shape[2]), int(x.shape[3])))
         return finc_inverse(x, self.weight, 4, _native.ORDERS_UNIT)
 
     def logdet(self, x, context=None):

@@ -155,8 +155,13 @@ class HotPathRunner:
 
     def __init__(self, stack: FincStack, batch: int, device, slots=1, lr=1e-3, host_io=False,
                  process_group=None, use_graphs=True, use_prepared=True, fused_collective=True,
-                 device_latents=False, overlap_sampling=False):
+                 device_latents=False, overlap_sampling=False, dense_inverse=False):
         self.stack, self.B, self.device = stack, batch, torch.device(device)
+        # dense_inverse: sampling with FIXED weights -- the deep, small levels (4x4 / 8x8 tiles, n = Cq*H*W <= 1024
+        # unknowns per group) run x = L^-1 z as tensor-core GEMMs (finc_inverse_dense_f32); L^-1 is rebuilt by
+        # prepare_dense() and NOT by the optimizer phase, so do not combine it with training steps
+        self.dense_inverse = dense_inverse
+        self.dense = {}
         self.pg = process_group
         self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)
         self.host_io, self.use_graphs = host_io, use_graphs
@@ -266,6 +271,35 @@ class HotPathRunner:
         for side in self.side[:min(k, self.N_SIDE)]:
             main.wait_stream(side)
 
+    def prepare_dense(self, max_n=1024):
+        """build the dense inverse tables (see dense_inverse) of the levels where the GEMM form is MEASURED faster
+        than the wavefront kernel at this batch size (k=5 and the 4x4 levels: 2-5x; 8x8 at k=3: about even)"""
+        self.dense = {}
+        if not self.dense_inverse:
+            return
+        for li, lv in enumerate(self.stack.levels):
+            n = lv.cq * lv.height * lv.width
+            if n > max_n or _native.inverse_dense_bytes(4, lv.cq, lv.height, lv.width) == 0:
+                continue
+            w0 = self.stack.unit_weight(li, 0).detach().contiguous()
+            blob = _native.inverse_dense_prepare(w0, lv.height, lv.width)
+            z = torch.randn(self.B, 4 * lv.cq, lv.height, lv.width, device=self.device)
+            out = torch.empty_like(z)
+            times = []
+            for fn in (lambda: _native.inverse(z, out=out, **self._w(li, 0, _native.PREP_INVERSE)), lambda: _native.inverse_dense(z, blob, out=out)):
+                for _ in range(2):
+                    fn()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    fn()
+                e1.record()
+                e1.synchronize()
+                times.append(e0.elapsed_time(e1))
+            if times[1] < times[0]:
+                self.dense[li] = [blob] + [_native.inverse_dense_prepare(self.stack.unit_weight(li, u).detach().contiguous(),
+                                                                         lv.height, lv.width) for u in range(1, lv.n_units)]
+
     def _w(self, li, u, kind):
         """keyword arguments selecting the raw weights or the prepared table of unit (li, u)"""
         if self.tables is None:
@@ -320,7 +354,7 @@ class HotPathRunner:
                                            **self._w(li, u, _native.PREP_BACKWARD_INPUT))
                     ready = torch.cuda.Event()
                     ready.record(main)
-        for side in self.side:
+        for side in self.side[:min(k, self.N_SIDE)]:   # only the streams that got work (a stream outside the capture cannot be joined)
             main.wait_stream(side)
 
     def _optimizer(self, s):
@@ -343,7 +377,10 @@ class HotPathRunner:
                 s.zin[li].normal_()
             src, cur = s.zin[li], 0
             for u in reversed(range(lv.n_units)):
-                _native.inverse(src, out=s.samp[li][cur], **self._w(li, u, _native.PREP_INVERSE))
+                if li in self.dense:
+                    _native.inverse_dense(src, self.dense[li][u], out=s.samp[li][cur])
+                else:
+                    _native.inverse(src, out=s.samp[li][cur], **self._w(li, u, _native.PREP_INVERSE))
                 src, cur = s.samp[li][cur], cur ^ 1
             s.sample_out[li] = src
 
@@ -371,6 +408,7 @@ class HotPathRunner:
 
     def _prepare_warm_and_capture(self):
         self._prepare_weights()
+        self.prepare_dense()
         for s in self.slots:
             if self.host_io:
                 self._copy_in(s)

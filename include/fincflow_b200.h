@@ -281,6 +281,19 @@ int finc_coupling_backward_f32(const float* x, const float* dy, const float* dlo
                                float* dw1, float* db1, float* dw2, float* db2, float* dw3, float* db3, float* dlogs3,
                                int B, int C, int H, int W, int width, unsigned flags, void* stream);
 
+/* Dense form of the inverse for the deep, small levels (n = C*H*W unknowns per (image, group), 64 <= n <= 1024,
+ * n % 64 == 0: the 4x4 and 8x8 tiles of the flows).  x = L^-1 z is the same linear map for every image, so a batch
+ * is one tensor-core GEMM per group (3xTF32, fp32 parity) instead of an anti-diagonal recurrence 4 .. 8 pixels wide.
+ * finc_inverse_dense_prepare_f32 builds L^-1 for every group by running finc_inverse_f32 on the identity -- once per
+ * weight update; `scratch` >= finc_inverse_dense_scratch_bytes.  Same result as finc_inverse_f32 up to fp32
+ * rounding; for sampling with fixed weights (fastflow/fastflow.py:78-100 called per layer per sample batch). */
+size_t finc_inverse_dense_bytes(int G, int C, int H, int W);           /* 0 = shape not covered */
+size_t finc_inverse_dense_scratch_bytes(int G, int C, int H, int W);
+int finc_inverse_dense_prepare_f32(const float* w, void* prepared, void* scratch, size_t scratch_bytes,
+                                   int G, int C, int H, int W, int kH, int kW, unsigned orders, void* stream);
+int finc_inverse_dense_f32(const float* z, const void* prepared, float* x, int B, int G, int C, int H, int W,
+                           unsigned flags, void* stream);
+
 /* Debug aid, inactive unless the environment has FINC_DEBUG_TS=1: the tiled kernels then record
  * per-CTA %globaltimer marks (8 slots per CTA); this call synchronises the device and copies them. */
 int finc_debug_timestamps(unsigned long long* host_out, int n);

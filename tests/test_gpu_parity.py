@@ -471,3 +471,49 @@ def test_no_out_of_bounds_writes(nat, shape):
         nat.squeeze(x, out=view.view(B, 4 * CT, H // 2, W // 2))
         torch.cuda.synchronize()
         check(buf, n, "squeeze")
+
+
+@pytest.mark.parametrize("case", [(300, 48, 8, 8, 5), (300, 48, 8, 8, 3), (257, 96, 4, 4, 5), (64, 96, 4, 4, 3), (100, 48, 4, 4, 3),
+                                  (33, 24, 8, 8, 3), (5, 16, 4, 4, 3)])
+def test_dense_inverse_matches_wavefront_inverse(case):
+    """finc_inverse_dense_f32 (x = L^-1 z as tensor-core GEMMs, L^-1 from the wavefront kernel on the identity)
+    is the same map as finc_inverse_f32: <= 1e-5 relative, <= 1e-4 round trip, and agrees with the oracle"""
+    from fincflow_b200 import _native
+    from fincflow_b200.fastflow import FastFlowUnit
+
+    B, C, H, W, k = case
+    torch.manual_seed(B + C)
+    unit = FastFlowUnit(C, C, (k, k)).cuda()
+    w = unit.weight.detach()
+    assert _native.inverse_dense_bytes(4, C // 4, H, W) > 0
+    blob = _native.inverse_dense_prepare(w, H, W)
+    z = torch.randn(B, C, H, W, device="cuda")
+    xd = _native.inverse_dense(z, blob)
+    xw = _native.inverse(z, w)
+    assert rel_err(xd.cpu().numpy(), xw.cpu().numpy()) <= REL_TOL
+    assert elementwise_close(xd.cpu().numpy(), xw.cpu().numpy())
+    zz, _ = _native.forward(xd, w, want_logdet=False)
+    assert float((zz - z).abs().max()) <= RT_TOL
+    if B <= 64:
+        assert rel_err(xd.cpu().numpy(), fo.inverse(z.cpu().numpy(), w.cpu().numpy())) <= REL_TOL
+    assert _native.inverse_dense_bytes(4, 3, 16, 16) > 0 and _native.inverse_dense_bytes(4, 3, 32, 32) == 0
+
+
+def test_fastflowunit_dense_reverse_is_cached_per_weight_version():
+    from fincflow_b200.fastflow import FastFlowUnit
+
+    torch.manual_seed(1)
+    unit = FastFlowUnit(48, 48, (5, 5)).cuda()
+    z = torch.randn(130, 48, 4, 4, device="cuda")
+    with torch.no_grad():
+        want = unit.reverse(z)
+        unit.dense_reverse = True
+        got = unit.reverse(z)
+        blob = unit._dense_blob
+        assert unit.reverse(z) is not None and unit._dense_blob is blob          # cached
+        assert rel_err(got.cpu().numpy(), want.cpu().numpy()) <= REL_TOL
+        unit.weight.mul_(1.01)                                                    # new version -> new table
+        got2 = unit.reverse(z)
+        unit.dense_reverse = False
+        assert rel_err(got2.cpu().numpy(), unit.reverse(z).cpu().numpy()) <= REL_TOL
+        assert rel_err(got2.cpu().numpy(), want.cpu().numpy()) > 1e-4

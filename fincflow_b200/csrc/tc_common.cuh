@@ -22,6 +22,20 @@ __device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
         if (spins > (1u << 26)) __trap();
     }
 }
+// non-blocking probe of a barrier phase (mbarrier.try_wait may suspend the thread for a while)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // one lane of a converged warp (the same lane every time): tcgen05.mma / tcgen05.commit / TMA issue
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;

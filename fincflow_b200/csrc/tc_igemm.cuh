@@ -210,41 +210,60 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
         {
             constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
+            // The tensor-core queue is shallow: tools/mma_issue_bench.cu shows that a pause of the issuing thread
+            // is hidden only up to ~100 cycles, and that ONE satisfied mbarrier wait costs ~100 cycles of latency
+            // (three waits + fence per k-block, as this loop was first written: 82 instead of 64 cycles per MMA).
+            // So the bookkeeping is done once per GROUP (the kFlush k-blocks of one TMEM partial): one polling
+            // loop probes the partial's `empty` barrier and the split barriers of all its k-blocks together (the
+            // probes overlap), and only a k-block that was not ready at that moment is waited for separately.
+            // xf[s] is arrived on by threads that have seen full[s], so it covers the weight tile as well.
             uint32_t it = 0, gq = 0;   // k-block counter, group (= partial) counter
             for (int ct = cluster_id; ct < cluster_tiles; ct += n_clusters) {
-                for (int kblk = 0; kblk < kblocks; ++kblk, ++it) {
-                    const int s = it % S;
-                    const uint32_t ph = (it / S) & 1;
-                    const int in_group = kblk % C::kFlush;
+                for (int kb0 = 0; kb0 < kblocks; kb0 += C::kFlush, ++gq) {
+                    const int nk = kblocks - kb0 < C::kFlush ? kblocks - kb0 : C::kFlush;
                     const uint32_t p = gq % NP;
-                    if (in_group == 0) {
-                        mbar_wait_long(&part_empty[p], ((gq / NP) & 1) ^ 1);
-                        tc_fence_after();
-                    }
                     const uint32_t d_tmem = tmem_base + p * BN;
-                    mbar_wait_long(&full[s], ph);   // weight tile landed
-                    mbar_wait_long(&xf[s], ph);     // activation tile split into TMEM
-                    tc_fence_after();
-                    const uint64_t db_hi = umma_desc_k_sw128(b_hi(s)), db_lo = umma_desc_k_sw128(b_lo(s));
-                    const uint32_t ta_hi = tmem_base + C::kAColBase + s * C::kACols, ta_lo = ta_hi + kBK;
-                    if (elect_one()) {
-                        // small terms first (a_lo*b_hi, a_hi*b_lo), the dominant product last
+                    uint32_t ready = 0;
+                    for (uint32_t spins = 0;; ++spins) {
+                        uint32_t m = mbar_try_wait(&part_empty[p], ((gq / NP) & 1) ^ 1) ? 1u : 0u;
+                        m |= mbar_try_wait(&xf[it % S], (it / S) & 1) ? 2u : 0u;
 #pragma unroll
-                        for (int pass = 0; pass < NPASS; ++pass) {
-#pragma unroll
-                            for (int k = 0; k < kBK / kUmmaK; ++k) {
-                                const uint64_t adv = (uint64_t)(k * kUmmaK * 4 >> 4);  // 32 bytes per K step inside the swizzle row
-                                const uint32_t acc = (in_group != 0 || pass != 0 || k != 0) ? 1u : 0u;
-                                const uint32_t ta = ((NPASS == 3 && pass == 0) ? ta_lo : ta_hi) + k * kUmmaK;
-                                const uint64_t db = (NPASS == 3 && pass == 1) ? db_lo : db_hi;
-                                umma_tf32_ts(d_tmem, ta, db + adv, idesc, acc);
-                            }
-                        }
-                        if (CL == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], kAllCtas);
-                        if (in_group == C::kFlush - 1 || kblk == kblocks - 1) umma_commit(&part_full[p]);
+                        for (int j = 1; j < C::kFlush; ++j)
+                            if (j < nk) m |= mbar_test_wait(&xf[(it + j) % S], ((it + j) / S) & 1) ? (2u << j) : 0u;
+                        ready = __reduce_and_sync(0xffffffffu, m);   // warp-uniform by construction
+                        if ((ready & 3u) == 3u) break;
+                        if (spins > (1u << 26)) __trap();
                     }
-                    __syncwarp();
-                    if (in_group == C::kFlush - 1 || kblk == kblocks - 1) ++gq;
+                    tc_fence_after();
+#pragma unroll
+                    for (int j = 0; j < C::kFlush; ++j) {
+                        if (j >= nk) break;
+                        const int s = (it + j) % S;
+                        if (j > 0 && !(ready & (2u << j))) {
+                            mbar_wait_long(&xf[s], ((it + j) / S) & 1);
+                            tc_fence_after();
+                        }
+                        const uint64_t db_hi = umma_desc_k_sw128(b_hi(s)), db_lo = umma_desc_k_sw128(b_lo(s));
+                        const uint32_t ta_hi = tmem_base + C::kAColBase + s * C::kACols, ta_lo = ta_hi + kBK;
+                        if (elect_one()) {
+                            // small terms first (a_lo*b_hi, a_hi*b_lo), the dominant product last
+#pragma unroll
+                            for (int pass = 0; pass < NPASS; ++pass) {
+#pragma unroll
+                                for (int k = 0; k < kBK / kUmmaK; ++k) {
+                                    const uint64_t adv = (uint64_t)(k * kUmmaK * 4 >> 4);  // 32 bytes per K step inside the swizzle row
+                                    const uint32_t acc = (j != 0 || pass != 0 || k != 0) ? 1u : 0u;
+                                    const uint32_t ta = ((NPASS == 3 && pass == 0) ? ta_lo : ta_hi) + k * kUmmaK;
+                                    const uint64_t db = (NPASS == 3 && pass == 1) ? db_lo : db_hi;
+                                    umma_tf32_ts(d_tmem, ta, db + adv, idesc, acc);
+                                }
+                            }
+                            if (CL == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], kAllCtas);
+                            if (j == nk - 1) umma_commit(&part_full[p]);
+                        }
+                        __syncwarp();
+                    }
+                    it += nk;
                 }
             }
         }

@@ -132,40 +132,54 @@ wgrad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ C
         }
     } else if (warp == 1) {
         constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
+        // bookkeeping once per group of kFlush k-blocks (see tc_igemm.cuh: every satisfied mbarrier wait in the
+        // issuing thread costs ~100 cycles that the shallow tensor-core queue cannot hide)
         uint32_t it = 0, gq = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-            for (int kb = 0; kb < g.kb_per_slice; ++kb, ++it) {
-                const int s = it % S;
-                const uint32_t ph = (it / S) & 1;
-                const int in_group = kb % C::kFlush;
+            for (int kb0 = 0; kb0 < g.kb_per_slice; kb0 += C::kFlush, ++gq) {
+                const int nk = g.kb_per_slice - kb0 < C::kFlush ? g.kb_per_slice - kb0 : C::kFlush;
                 const uint32_t p = gq % NP;
-                if (in_group == 0) {
-                    mbar_wait_long(&part_empty[p], ((gq / NP) & 1) ^ 1);
-                    tc_fence_after();
-                }
                 const uint32_t d_tmem = tmem_base + p * BN;
-                mbar_wait_long(&xf[s], ph);   // both operands split (implies the TMA bytes landed)
-                tc_fence_after();
-                const uint64_t db_hi = umma_desc_k_sw128(q_hi(s)), db_lo = umma_desc_k_sw128(q_lo(s));
-                const uint32_t ta_hi = tmem_base + C::kAColBase + s * C::kACols, ta_lo = ta_hi + kBK;
-                const bool last = in_group == C::kFlush - 1 || kb == g.kb_per_slice - 1;
-                if (elect_one()) {
+                uint32_t ready = 0;
+                for (uint32_t spins = 0;; ++spins) {
+                    uint32_t m = mbar_try_wait(&part_empty[p], ((gq / NP) & 1) ^ 1) ? 1u : 0u;
+                    m |= mbar_try_wait(&xf[it % S], (it / S) & 1) ? 2u : 0u;   // both operands split (implies the TMA bytes landed)
 #pragma unroll
-                    for (int pass = 0; pass < NPASS; ++pass) {
-#pragma unroll
-                        for (int k = 0; k < kBK / kUmmaK; ++k) {
-                            const uint64_t adv = (uint64_t)(k * kUmmaK * 4 >> 4);   // 8 pixels = 32 bytes inside the swizzle row
-                            const uint32_t acc = (in_group != 0 || pass != 0 || k != 0) ? 1u : 0u;
-                            const uint32_t ta = ((NPASS == 3 && pass == 0) ? ta_lo : ta_hi) + k * kUmmaK;
-                            const uint64_t db = (NPASS == 3 && pass == 1) ? db_lo : db_hi;
-                            umma_tf32_ts(d_tmem, ta, db + adv, idesc, acc);
-                        }
-                    }
-                    umma_commit(&empty[s]);
-                    if (last) umma_commit(&part_full[p]);
+                    for (int j = 1; j < C::kFlush; ++j)
+                        if (j < nk) m |= mbar_test_wait(&xf[(it + j) % S], ((it + j) / S) & 1) ? (2u << j) : 0u;
+                    ready = __reduce_and_sync(0xffffffffu, m);
+                    if ((ready & 3u) == 3u) break;
+                    if (spins > (1u << 26)) __trap();
                 }
-                __syncwarp();
-                if (last) ++gq;
+                tc_fence_after();
+#pragma unroll
+                for (int j = 0; j < C::kFlush; ++j) {
+                    if (j >= nk) break;
+                    const int s = (it + j) % S;
+                    if (j > 0 && !(ready & (2u << j))) {
+                        mbar_wait_long(&xf[s], ((it + j) / S) & 1);
+                        tc_fence_after();
+                    }
+                    const uint64_t db_hi = umma_desc_k_sw128(q_hi(s)), db_lo = umma_desc_k_sw128(q_lo(s));
+                    const uint32_t ta_hi = tmem_base + C::kAColBase + s * C::kACols, ta_lo = ta_hi + kBK;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int pass = 0; pass < NPASS; ++pass) {
+#pragma unroll
+                            for (int k = 0; k < kBK / kUmmaK; ++k) {
+                                const uint64_t adv = (uint64_t)(k * kUmmaK * 4 >> 4);   // 8 pixels = 32 bytes inside the swizzle row
+                                const uint32_t acc = (j != 0 || pass != 0 || k != 0) ? 1u : 0u;
+                                const uint32_t ta = ((NPASS == 3 && pass == 0) ? ta_lo : ta_hi) + k * kUmmaK;
+                                const uint64_t db = (NPASS == 3 && pass == 1) ? db_lo : db_hi;
+                                umma_tf32_ts(d_tmem, ta, db + adv, idesc, acc);
+                            }
+                        }
+                        umma_commit(&empty[s]);
+                        if (j == nk - 1) umma_commit(&part_full[p]);
+                    }
+                    __syncwarp();
+                }
+                it += nk;
             }
         }
     } else if (warp < 6) {

@@ -598,10 +598,12 @@ def main_ours(args):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_value = B * world * K / (e2e_ms * 1e-3)
-    act_bytes = sum(4 * B * lv.dim for lv in lvls)
-    h2d = act_bytes                                      # the data batch x of every level (the sampling latents are
-                                                         # drawn on the device, like the reference's model.sample)
-    d2h = act_bytes + sum(4 * B for _ in lvls)           # samples + logp
+    # counted from the slabs HotPathRunner.step copies: ONE host->device copy (the data batch x of every level; the
+    # sampling latents are drawn on the device, like the reference's model.sample) and ONE device->host copy
+    # (logp + samples of every level) per step
+    slot0 = e2e_runner.slots[0]
+    h2d = 4 * slot0.n_x
+    d2h = 4 * slot0.out_dev.numel()
     launches = e2e_runner.launches_per_step
     fused_flag = getattr(e2e_runner, "fused_collective", False)
     crossrank = None
@@ -687,6 +689,7 @@ def main_ours(args):
                 "inverse_sampling": round(B * world / (pm["inverse"] * 1e-3))},
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_ms / K, 4), "api": "fincflow_b200.stack.HotPathRunner(host_io=True).step",
+                    "copies_per_step": {"h2d": 1, "d2h": 1},
                     "host_enqueue_ms_per_step": round(host_ms_per_step, 4), "host_cpus": host_cpus,
                     "check_mean_logp_level0": logp_last},
             "gpu_launches": launches * K,

@@ -116,8 +116,27 @@ class FincStack(nn.Module):
         return z
 
 
+def _carve(flat, shapes, align=64):
+    """views of the given shapes into one flat fp32 buffer, each starting on a 256-byte boundary"""
+    out, off = [], 0
+    for shp in shapes:
+        n = math.prod(shp)
+        out.append(flat[off:off + n].view(shp))
+        off += (n + align - 1) // align * align
+    return out
+
+
+def _carved_numel(shapes, align=64):
+    return sum((math.prod(shp) + align - 1) // align * align for shp in shapes)
+
+
 class _Slot:
-    """static device buffers of one input slot (graphs replay on fixed addresses)"""
+    """static device buffers of one input slot (graphs replay on fixed addresses).
+
+    Everything that crosses PCIe lives in two contiguous slabs per direction: `in_dev` / `in_host` hold the data
+    batch of every level followed by the sampling latents of every level, `out_dev` / `out_host` the per-sample
+    log-likelihoods followed by the generated samples -- a step is ONE host->device and ONE device->host copy
+    (round 1 issued 3 + 6 small ones per step; at 8 ranks behind one host that cost 20 % of the end-to-end rate)."""
 
     def __init__(self, stack, B, device, pinned):
         f = dict(dtype=torch.float32, device=device)
@@ -125,19 +144,30 @@ class _Slot:
         self.x_host, self.z_host, self.logp_host, self.samp_host = [], [], [], []
         self.sample_out = {}
         self.ev_in, self.ev_computed, self.ev_out, self.ev_samp = (torch.cuda.Event() for _ in range(4))
-        for lv in stack.levels:
-            shp = (B, lv.channels, lv.height, lv.width)
-            self.acts.append([torch.zeros(shp, **f) for _ in range(lv.n_units + 1)])
+        shapes = [(B, lv.channels, lv.height, lv.width) for lv in stack.levels]
+        in_shapes = shapes + shapes                       # x of every level, then z of every level
+        out_shapes = [(B,) for _ in shapes] + shapes      # logp of every level, then the samples
+        self.n_x = _carved_numel(shapes)                  # the x part of the input slab (device_latents: only this is copied)
+        self.in_dev = torch.zeros(_carved_numel(in_shapes), **f)
+        self.out_dev = torch.zeros(_carved_numel(out_shapes), **f)
+        in_views, out_views = _carve(self.in_dev, in_shapes), _carve(self.out_dev, out_shapes)
+        L = len(shapes)
+        for li, (lv, shp) in enumerate(zip(stack.levels, shapes)):
+            self.acts.append([in_views[li]] + [torch.zeros(shp, **f) for _ in range(lv.n_units)])
             self.logdet.append(torch.zeros(B, **f))
-            self.logp.append(torch.zeros(B, **f))
+            self.logp.append(out_views[li])
             self.dzs.append([torch.zeros(shp, **f) for _ in range(lv.n_units + 1)])  # dzs[u] = dL/d acts[u]
-            self.zin.append(torch.zeros(shp, **f))
-            self.samp.append([torch.zeros(shp, **f) for _ in range(2)])
-            if pinned:
-                self.x_host.append(torch.zeros(shp, dtype=torch.float32).pin_memory())
-                self.z_host.append(torch.zeros(shp, dtype=torch.float32).pin_memory())
-                self.logp_host.append(torch.zeros(B, dtype=torch.float32).pin_memory())
-                self.samp_host.append(torch.zeros(shp, dtype=torch.float32).pin_memory())
+            self.zin.append(in_views[L + li])
+            # the inverse chain ping-pongs between two buffers; the one its LAST unit writes is the slab view
+            pp = [torch.zeros(shp, **f), torch.zeros(shp, **f)]
+            pp[(lv.n_units - 1) % 2] = out_views[L + li]
+            self.samp.append(pp)
+        if pinned:
+            self.in_host = torch.zeros(self.in_dev.numel(), dtype=torch.float32).pin_memory()
+            self.out_host = torch.zeros(self.out_dev.numel(), dtype=torch.float32).pin_memory()
+            hin, hout = _carve(self.in_host, in_shapes), _carve(self.out_host, out_shapes)
+            self.x_host, self.z_host = hin[:L], hin[L:]
+            self.logp_host, self.samp_host = hout[:L], hout[L:]
 
 
 class HotPathRunner:
@@ -155,8 +185,14 @@ class HotPathRunner:
 
     def __init__(self, stack: FincStack, batch: int, device, slots=1, lr=1e-3, host_io=False,
                  process_group=None, use_graphs=True, use_prepared=True, fused_collective=True,
-                 device_latents=False, overlap_sampling=False, dense_inverse=False):
+                 device_latents=False, overlap_sampling=False, dense_inverse=False, level_parallel=False):
         self.stack, self.B, self.device = stack, batch, torch.device(device)
+        # level_parallel: the levels of a FincStack have independent inputs, so their unit chains (forward,
+        # dX, inverse) may run next to each other -- one stream per level, forked from and joined to the
+        # current stream (inside a graph: parallel branches).  Batch-256 launches are latency-bound and do not
+        # fill the GPU, so the chains overlap.  Off by default: per-phase launch durations stay clean.
+        self.level_parallel = level_parallel and len(stack.levels) > 1
+        self.level_streams = [torch.cuda.Stream(torch.device(device)) for _ in stack.levels] if self.level_parallel else None
         # dense_inverse: sampling with FIXED weights -- the deep, small levels (4x4 / 8x8 tiles, n = Cq*H*W <= 1024
         # unknowns per group) run x = L^-1 z as tensor-core GEMMs (finc_inverse_dense_f32); L^-1 is rebuilt by
         # prepare_dense() and NOT by the optimizer phase, so do not combine it with training steps
@@ -308,37 +344,58 @@ class HotPathRunner:
 
     # ---- the four phases as plain launch sequences on the current stream ----------------------
     def _copy_in(self, s):
-        """host -> device: this step's data batch (x) and sampling latents (z) of every level"""
-        for li in range(len(self.stack.levels)):
-            s.acts[li][0].copy_(s.x_host[li], non_blocking=True)
-            if not self.device_latents:
-                s.zin[li].copy_(s.z_host[li], non_blocking=True)
+        """host -> device, ONE copy: this step's data batch (x) and sampling latents (z) of every level"""
+        n = s.n_x if self.device_latents else s.in_dev.numel()
+        s.in_dev[:n].copy_(s.in_host[:n], non_blocking=True)
 
     def _copy_out(self, s):
-        """device -> host: per-sample log-likelihoods and the generated samples of every level"""
-        for li in range(len(self.stack.levels)):
-            s.logp_host[li].copy_(s.logp[li], non_blocking=True)
-            s.samp_host[li].copy_(s.sample_out[li], non_blocking=True)
+        """device -> host, ONE copy: per-sample log-likelihoods and the generated samples of every level"""
+        s.out_host.copy_(s.out_dev, non_blocking=True)
+
+    def _per_level(self, body):
+        """run body(li, lv) for every level: in order on the current stream, or (level_parallel) each level on
+        its own stream between a fork and a join on the current stream"""
+        levels = list(enumerate(self.stack.levels))
+        if not self.level_parallel:
+            for li, lv in levels:
+                body(li, lv)
+            return
+        main = torch.cuda.current_stream(self.device)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for li, lv in levels:
+            ls = self.level_streams[li]
+            ls.wait_event(fork)
+            with torch.cuda.stream(ls):
+                body(li, lv)
+        for ls in self.level_streams:
+            main.wait_stream(ls)
 
     def _forward(self, s):
-        st = self.stack
-        for li, lv in enumerate(st.levels):
-            for u in range(lv.n_units):
-                flags = _native.FLAG_LOGDET_ACCUMULATE if u else 0
-                _native.forward(s.acts[li][u], flags=flags, out=s.acts[li][u + 1], logdet_out=s.logdet[li],
-                                **self._w(li, u, _native.PREP_FORWARD))
-            # logp and dz = d(-mean_n logp)/dz = z / (B * world)
-            _native.gaussian_logp(s.acts[li][lv.n_units], s.logdet[li], 1.0 / (self.B * self.world),
-                                  logp_out=s.logp[li], dz_out=s.dzs[li][lv.n_units])
+        self._per_level(lambda li, lv: self._forward_level(s, li, lv))
+
+    def _forward_level(self, s, li, lv):
+        for u in range(lv.n_units):
+            flags = _native.FLAG_LOGDET_ACCUMULATE if u else 0
+            _native.forward(s.acts[li][u], flags=flags, out=s.acts[li][u + 1], logdet_out=s.logdet[li],
+                            **self._w(li, u, _native.PREP_FORWARD))
+        # logp and dz = d(-mean_n logp)/dz = z / (B * world)
+        _native.gaussian_logp(s.acts[li][lv.n_units], s.logdet[li], 1.0 / (self.B * self.world),
+                              logp_out=s.logp[li], dz_out=s.dzs[li][lv.n_units])
 
     def _backward(self, s):
         """dX chain on the current stream; the masked dW of every unit -- written straight into
         the flat gradient bucket -- on side streams as soon as its dz exists.
         dzs[u] = dL/d acts[u]; the data gradient of unit 0 is never needed."""
         st = self.stack
-        main = torch.cuda.current_stream(self.device)
-        k = 0
-        for li, lv in enumerate(st.levels):
+        outer = torch.cuda.current_stream(self.device)
+        base = [0]
+        for lv in st.levels:
+            base.append(base[-1] + lv.n_units)
+
+        def level(li, lv):
+            main = torch.cuda.current_stream(self.device)
+            k = base[li]
             ready = torch.cuda.Event()
             ready.record(main)                      # dzs[n] comes from the forward phase
             for u in reversed(range(lv.n_units)):
@@ -354,8 +411,10 @@ class HotPathRunner:
                                            **self._w(li, u, _native.PREP_BACKWARD_INPUT))
                     ready = torch.cuda.Event()
                     ready.record(main)
-        for side in self.side[:min(k, self.N_SIDE)]:   # only the streams that got work (a stream outside the capture cannot be joined)
-            main.wait_stream(side)
+
+        self._per_level(level)
+        for side in self.side[:min(base[-1], self.N_SIDE)]:   # only the streams that got work (a stream outside the capture cannot be joined)
+            outer.wait_stream(side)
 
     def _optimizer(self, s):
         if self.fused_collective:
@@ -371,18 +430,19 @@ class HotPathRunner:
         self._prepare_weights()
 
     def _inverse(self, s):
-        st = self.stack
-        for li, lv in enumerate(st.levels):
-            if self.device_latents:
-                s.zin[li].normal_()
-            src, cur = s.zin[li], 0
-            for u in reversed(range(lv.n_units)):
-                if li in self.dense:
-                    _native.inverse_dense(src, self.dense[li][u], out=s.samp[li][cur])
-                else:
-                    _native.inverse(src, out=s.samp[li][cur], **self._w(li, u, _native.PREP_INVERSE))
-                src, cur = s.samp[li][cur], cur ^ 1
-            s.sample_out[li] = src
+        self._per_level(lambda li, lv: self._inverse_level(s, li, lv))
+
+    def _inverse_level(self, s, li, lv):
+        if self.device_latents:
+            s.zin[li].normal_()
+        src, cur = s.zin[li], 0
+        for u in reversed(range(lv.n_units)):
+            if li in self.dense:
+                _native.inverse_dense(src, self.dense[li][u], out=s.samp[li][cur])
+            else:
+                _native.inverse(src, out=s.samp[li][cur], **self._w(li, u, _native.PREP_INVERSE))
+            src, cur = s.samp[li][cur], cur ^ 1
+        s.sample_out[li] = src
 
     def _phase_fns(self):
         return (self._forward, self._backward, self._optimizer, self._inverse)

@@ -137,6 +137,38 @@ def run_extra_workloads(torch, dev, world, rank, pg, K, names=None):
     return out
 
 
+def fused_vs_nccl_check(torch, dev, rank, pg):
+    """N > 1: three training steps of a small stack through the fused NVLink all-reduce + Adam kernel and through
+    NCCL all-reduce + Adam from identical states: max |parameter difference| between the two paths (fp32 summation
+    order differs: <= 1e-5) -- the driver-visible form of tests/multirank_check.py"""
+    from fincflow_b200.stack import FincStack, HotPathRunner, LevelSpec
+
+    try:
+        lv = [LevelSpec(12, 8, 8, 3, (3, 3)), LevelSpec(24, 4, 4, 2, (3, 3))]
+        res = {}
+        for fused in (True, False):
+            torch.manual_seed(0)
+            stack = FincStack(lv).to(dev)
+            runner = HotPathRunner(stack, 8, dev, slots=1, lr=1e-2, process_group=pg, fused_collective=fused)
+            if fused and not runner.fused_collective:
+                return {"skipped": getattr(runner, "fused_collective_error", "no peer memory")}
+            g = torch.Generator(device=dev).manual_seed(100 + rank)
+            for li in range(len(lv)):
+                runner.slots[0].acts[li][0].normal_(generator=g)
+                runner.slots[0].zin[li].normal_(generator=g)
+            runner.prepare()          # side-effect free: parameters and Adam state are restored
+            for _ in range(3):
+                runner.step(0)
+            torch.cuda.synchronize(dev)
+            res[fused] = stack.flat.detach().clone()
+            del runner
+        d = (res[True] - res[False]).abs().max().reshape(1).double()
+        torch.distributed.all_reduce(d, op=torch.distributed.ReduceOp.MAX)
+        return {"max_abs_param_diff": float(d.item()), "steps": 3}
+    except Exception as e:
+        return {"error": repr(e)}
+
+
 def gpu_reference_detail(torch, dev, ours_phase_ms):
     """the REFERENCE's own GPU path on the same box, same step: F.pad + conv2d fwd / autograd bwd with TF32
     off + `grad * mask` + Adam, and FastFlowUnit.reverse_level2 on the reference's CUDA extension (compiled
@@ -405,7 +437,7 @@ def whole_flow_detail(torch, dev, world=1, rank=0, pg=None):
     torch.manual_seed(0)
     B = PER_GPU_BATCH
     m = flows.fastflow_cifar10(actnorm=True).to(dev)
-    trainer = FlowTrainer(m, lr=1e-3, process_group=pg, use_graph=(world == 1))
+    trainer = FlowTrainer(m, lr=1e-3, process_group=pg, use_graph=os.environ.get("FINC_TRAINER_GRAPH", "1") == "1")
     g = torch.Generator(device=dev).manual_seed(7000 + rank)
     x = torch.randint(0, 256, (B, 3, 32, 32), device=dev, generator=g).float()
 
@@ -424,8 +456,9 @@ def whole_flow_detail(torch, dev, world=1, rank=0, pg=None):
                     f"batch {B} per GPU, random init, synthetic uint8 images; all layers on our kernels "
                     "(Coupling: tcgen05 3xTF32 GEMMs, fp32 parity)",
            "n_params": sum(p.numel() for p in m.parameters()), "per_gpu_batch": B, "global_batch": B * world}
-    out["train_step_execution"] = ("whole step (forward, backward, Adam) replayed as ONE CUDA graph" if world == 1 else
-                                   "eager; bucketed NCCL all-reduce launched from autograd hooks, overlapped with backward")
+    out["train_step_execution"] = ("whole step (forward, backward" + (", bucketed NCCL all-reduces launched from the autograd hooks" if world > 1 else "")
+                                   + ", Adam) replayed as ONE CUDA graph") if trainer.use_graph else \
+        "eager; bucketed NCCL all-reduce launched from autograd hooks, overlapped with backward"
     for name, fn, n in (("train_step", train, 6), ("eval_loglik", evaluate, 5), ("sample", sample, 5)):
         for _ in range(5 if name == "train_step" else 2):
             fn()
@@ -465,6 +498,7 @@ def whole_flow_detail(torch, dev, world=1, rank=0, pg=None):
     except Exception as e:
         out["graph_error"] = repr(e)
     out["replica_param_maxdiff"] = trainer.replica_max_diff()
+    trainer.close()   # the step graph holds NCCL work: it must go before the process group does
     out["round1_same_model_pytorch_glue"] = {"train_step_ms": 90.9, "sample_ms": 35.1,
                                              "note": "BENCH_r01: coupling networks through PyTorch/cuDNN (TF32)"}
     del m, trainer
@@ -614,6 +648,7 @@ def main_ours(args):
         dmax = (stack.flat.detach() - ref_w).abs().max().reshape(1).double()
         torch.distributed.all_reduce(dmax, op=torch.distributed.ReduceOp.MAX)
         crossrank = float(dmax.item())
+    fused_vs_nccl = fused_vs_nccl_check(torch, dev, rank, pg) if world > 1 else None
     e2e_runner_keep = e2e_runner
     del e2e_runner
     sampler.stop_flag = True
@@ -698,14 +733,23 @@ def main_ours(args):
             "cpu_baseline": cpu,
             "clocks": clocks,
             "crossrank_param_maxdiff": crossrank,
+            "fused_vs_nccl_maxdiff": fused_vs_nccl,
             "extra_workloads": extras,
             "gpu_reference": gpu_ref,
             "overlapped_sampling": overlap, "kernels": detail, "cfg3_full_flow": whole,
         }
         emit(line)
     if world > 1:
+        # teardown must never hold the job: the line is out; if communicator teardown stalls, leave after 30 s
+        import threading
+
+        sys.stdout.flush()
+        t = threading.Timer(30.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
+        t.cancel()
     return 0
 
 

@@ -17,9 +17,10 @@ reduce gradients to GPU 0, step there) done the torch.distributed way:
     all-reduces count / sum / sum of squares), so replicas start identical (the reference initialises on
     replica 0's shard: layers/actnorm.py:17-23);
   * sampling and likelihood evaluation use no collective;
-  * `use_graph=True` (single process): after `graph_warmup` eager steps the whole step -- forward, backward,
-    optimizer -- is captured into ONE CUDA graph and replayed (an eager step of the CIFAR-10 flow issues ~6000
-    kernel launches; the host, not the GPU, was the limit: 61 ms of CPU for 52 ms of GPU work).
+  * `use_graph=True`: after `graph_warmup` eager steps the whole step -- forward, backward, the bucketed NCCL
+    all-reduces launched from the autograd hooks, optimizer -- is captured into ONE CUDA graph and replayed (an
+    eager step of the CIFAR-10 flow issues ~6000 kernel launches; the host, not the GPU, was the limit: 61 ms of
+    CPU for 52 ms of GPU work).  Every rank must call step() the same number of times.
 """
 from __future__ import annotations
 
@@ -97,7 +98,7 @@ class FlowTrainer:
     # ---- one optimisation step ----------------------------------------------------------------------
     def step(self, x):
         """x = this rank's shard.  Returns the global mean negative log-likelihood (a 0-dim tensor)."""
-        if not (self.use_graph and self.world == 1 and x.is_cuda):
+        if not (self.use_graph and x.is_cuda):
             return self._step_eager(x)
         if self._graph is not None and tuple(x.shape) == tuple(self._static_x.shape):
             self._static_x.copy_(x)
@@ -108,11 +109,14 @@ class FlowTrainer:
             return self._step_eager(x)         # ActNorm initialisation, lazy kernel attributes, Adam state
         self._static_x = x.clone()
         torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.pg)        # every rank captures the same sequence of collectives
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._static_loss = self._step_eager(self._static_x)
         self._graph = g
-        return self._static_loss              # capture executed nothing: the step runs from the next call on
+        g.replay()                             # capture executed nothing: run the captured step once for this call
+        return self._static_loss
 
     def _step_eager(self, x):
         self.flat_grad.zero_()
@@ -140,6 +144,14 @@ class FlowTrainer:
             loss = loss.detach().clone()
             dist.all_reduce(loss, group=self.pg)
         return loss.detach()
+
+    def close(self):
+        """drop the captured graph (it references the process group's NCCL communicator: destroy the graph BEFORE
+        the process group, or communicator teardown waits for it forever)"""
+        if self._graph is not None:
+            torch.cuda.synchronize()
+            self._graph = None
+            self._static_x = self._static_loss = None
 
     # ---- checks ---------------------------------------------------------------------------------------
     def replica_max_diff(self):

@@ -322,17 +322,7 @@ def test_flow_trainer_graph_step_equals_eager_step():
     l_e, p_e, _ = run(False)
     l_g, p_g, tr = run(True)
     assert tr._graph is not None
-    # the call that captures runs nothing (its loss is the first replay's); compare the steps both executed
-    assert np.allclose(l_e[:2], l_g[:2], rtol=1e-6)
-    assert all(np.isfinite(l_g))
-    # graph run executed 5 optimizer steps (capture call skipped), eager 6: compare against a 5-step eager run
-    torch.manual_seed(5)
-    m = flows.FastFlow(n_blocks=2, block_size=2, image_size=(3, 16, 16), actnorm=True, width=128).cuda()
-    tr2 = FlowTrainer(m, lr=1e-3)
-    g = torch.Generator(device="cuda").manual_seed(9)
-    xs = [torch.randint(0, 256, (8, 3, 16, 16), device="cuda", generator=g).float() for _ in range(6)]
-    m.preprocess.layers[0].fixed_noise = torch.full((8, 3, 16, 16), 0.5, device="cuda")
-    for i in (0, 1, 3, 4, 5):
-        tr2.step(xs[i])
-    for a, b in zip(p_g, m.parameters()):
+    # the capturing call replays the graph once, so every call is exactly one optimizer step: same trajectory
+    assert np.allclose(l_e, l_g, rtol=1e-4)
+    for a, b in zip(p_g, p_e):
         assert rel_err(a.cpu().numpy(), b.detach().cpu().numpy()) <= 1e-4

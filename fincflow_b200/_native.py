@@ -25,6 +25,7 @@ FLAG_LOGDET_ACCUMULATE = 8
 FLAG_GENERIC_TILED = 16
 FLAG_WORKSPACE_CLEAN = 32
 FLAG_PREPARED = 64
+FLAG_CHAIN_TRANSPOSE = 2048
 FLAG_QUARTER_GPU = 128
 FLAG_HALF_GPU = 256
 FLAG_WAVE_SMEM = 512
@@ -43,7 +44,7 @@ SYMBOLS = (
     "finc_tc_wgrad_workspace_bytes", "finc_tc_wgrad_f32", "finc_coupling_prepared_bytes", "finc_coupling_workspace_bytes", "finc_coupling_prepare_f32",
     "finc_coupling_apply_f32", "finc_coupling_backward_workspace_bytes", "finc_coupling_backward_f32",
     "finc_inverse_dense_bytes", "finc_inverse_dense_scratch_bytes", "finc_inverse_dense_prepare_f32",
-    "finc_inverse_dense_f32",
+    "finc_inverse_dense_f32", "finc_chain_supported", "finc_chain_f32",
 )
 
 _lib = None
@@ -127,6 +128,10 @@ def load():
     lib.finc_inverse_dense_prepare_f32.argtypes = [p, p, p, sz, i, i, i, i, i, i, u, p]
     lib.finc_inverse_dense_f32.restype = i
     lib.finc_inverse_dense_f32.argtypes = [p, p, p, i, i, i, i, i, u, p]
+    lib.finc_chain_supported.restype = i
+    lib.finc_chain_supported.argtypes = [i, i, i, i, i, i, i]
+    lib.finc_chain_f32.restype = i
+    lib.finc_chain_f32.argtypes = [p, p, ctypes.c_long, p, ctypes.c_long, p, p, p, i, i, i, i, i, i, i, u, i, i, i, u, p]
     lib.finc_coupling_backward_workspace_bytes.restype = sz
     lib.finc_coupling_backward_workspace_bytes.argtypes = [i, i, i, i, i]
     lib.finc_coupling_backward_f32.restype = i
@@ -603,6 +608,54 @@ def inverse_dense(z, blob, G=4, flags=0, out=None):
     _check(load().finc_inverse_dense_f32(z.data_ptr(), blob.data_ptr(), x.data_ptr(), B, G, CT // G, H, W, flags,
                                          _stream(z)), "finc_inverse_dense_f32", G)
     return x
+
+
+def chain_supported(G, C, H, W, ksize=(3, 3), with_affine=False) -> bool:
+    return bool(load().finc_chain_supported(G, C, H, W, int(ksize[0]), int(ksize[1]), 1 if with_affine else 0))
+
+
+def chain(x, w_units, out, G=4, orders=ORDERS_UNIT, A=None, bias=None, logdet_out=None, units=None, transpose=False,
+          flags=0):
+    """A chain of FInC units in ONE launch (C ABI: finc_chain_f32).
+
+    x [B, G*C, H, W]; w_units [U, G*C, C, 3, 3] (contiguous); `units` = the unit indices in the order they are
+    applied (an arithmetic sequence; default 0..U-1).  out [U, B, G*C, H, W]: unit u writes out[u]; or out
+    [B, G*C, H, W]: only the result of the last unit is kept.  A [U, GC, GC] / bias [U, GC]: the affine map applied
+    after each unit.  transpose=True: each unit's backward-data map.  logdet_out [B]: the chain's FInC logdet."""
+    x = _prep(x, "x")
+    w_units = _prep(w_units, "weights")
+    _bind_device(x)
+    U = int(w_units.shape[0])
+    units = list(range(U)) if units is None else list(units)
+    n = len(units)
+    step = units[1] - units[0] if n > 1 else 1
+    if (n > 1 and step == 0) or any(units[i + 1] - units[i] != step for i in range(n - 1)) or min(units) < 0 or max(units) >= U:
+        raise FincNativeError("chain: `units` must be an arithmetic sequence inside [0, U)")
+    B, CT, H, W = (int(v) for v in x.shape)
+    C = CT // G
+    if tuple(w_units.shape[1:]) != (CT, C, 3, 3):
+        raise FincNativeError(f"chain: weights {tuple(w_units.shape)} do not match x {tuple(x.shape)} with G={G}")
+    if out.dim() == 5:
+        if tuple(out.shape) != (U, B, CT, H, W) or not out.is_contiguous():
+            raise FincNativeError("chain: out must be a contiguous [U, B, G*C, H, W] tensor")
+        y_stride = B * CT * H * W
+    else:
+        if tuple(out.shape) != tuple(x.shape) or not out.is_contiguous():
+            raise FincNativeError("chain: out must be contiguous and shaped like x")
+        y_stride = 0
+    if (A is None) != (bias is None):
+        raise FincNativeError("chain: A and bias come together")
+    if A is not None:
+        A, bias = _prep(A, "A"), _prep(bias, "bias")
+        if tuple(A.shape) != (U, CT, CT) or tuple(bias.shape) != (U, CT):
+            raise FincNativeError("chain: A must be [U, GC, GC] and bias [U, GC]")
+    if transpose:
+        flags |= FLAG_CHAIN_TRANSPOSE
+    _check(load().finc_chain_f32(x.data_ptr(), w_units.data_ptr(), CT * C * 9, out.data_ptr(), y_stride,
+                                 0 if A is None else A.data_ptr(), 0 if bias is None else bias.data_ptr(),
+                                 0 if logdet_out is None else logdet_out.data_ptr(), B, G, C, H, W, 3, 3, orders,
+                                 n, units[0], step, flags, _stream(x)), "finc_chain_f32")
+    return out
 
 
 def sm_count() -> int:

@@ -142,6 +142,7 @@ class _Slot:
         f = dict(dtype=torch.float32, device=device)
         self.acts, self.logdet, self.logp, self.dzs, self.samp, self.zin = [], [], [], [], [], []
         self.x_host, self.z_host, self.logp_host, self.samp_host = [], [], [], []
+        self.acts_blk, self.dzs_blk = [], []
         self.sample_out = {}
         self.ev_in, self.ev_computed, self.ev_out, self.ev_samp = (torch.cuda.Event() for _ in range(4))
         shapes = [(B, lv.channels, lv.height, lv.width) for lv in stack.levels]
@@ -153,10 +154,16 @@ class _Slot:
         in_views, out_views = _carve(self.in_dev, in_shapes), _carve(self.out_dev, out_shapes)
         L = len(shapes)
         for li, (lv, shp) in enumerate(zip(stack.levels, shapes)):
-            self.acts.append([in_views[li]] + [torch.zeros(shp, **f) for _ in range(lv.n_units)])
+            # acts[u + 1] (output of unit u) and dzs[u] are slices of ONE tensor per level: the chain kernel writes
+            # unit u's result at base + u * stride
+            blk = torch.zeros((lv.n_units,) + shp, **f)
+            self.acts_blk.append(blk)
+            self.acts.append([in_views[li]] + [blk[u] for u in range(lv.n_units)])
             self.logdet.append(torch.zeros(B, **f))
             self.logp.append(out_views[li])
-            self.dzs.append([torch.zeros(shp, **f) for _ in range(lv.n_units + 1)])  # dzs[u] = dL/d acts[u]
+            dblk = torch.zeros((lv.n_units + 1,) + shp, **f)
+            self.dzs_blk.append(dblk)
+            self.dzs.append([dblk[u] for u in range(lv.n_units + 1)])  # dzs[u] = dL/d acts[u]
             self.zin.append(in_views[L + li])
             # the inverse chain ping-pongs between two buffers; the one its LAST unit writes is the slab view
             pp = [torch.zeros(shp, **f), torch.zeros(shp, **f)]
@@ -185,8 +192,13 @@ class HotPathRunner:
 
     def __init__(self, stack: FincStack, batch: int, device, slots=1, lr=1e-3, host_io=False,
                  process_group=None, use_graphs=True, use_prepared=True, fused_collective=True,
-                 device_latents=False, overlap_sampling=False, dense_inverse=False, level_parallel=False):
+                 device_latents=False, overlap_sampling=False, dense_inverse=False, level_parallel=False, chain=True):
         self.stack, self.B, self.device = stack, batch, torch.device(device)
+        # chain: the forward pass of a level and its backward-data chain are ONE launch each (finc_chain_f32: the
+        # image tiles stay in shared memory between units; all activations are still written) wherever the shape
+        # is covered; bit-identical to the per-unit launches
+        self.chain = [chain and _native.chain_supported(4, lv.cq, lv.height, lv.width, lv.kernel_size)
+                      for lv in stack.levels]
         # level_parallel: the levels of a FincStack have independent inputs, so their unit chains (forward,
         # dX, inverse) may run next to each other -- one stream per level, forked from and joined to the
         # current stream (inside a graph: parallel branches).  Batch-256 launches are latency-bound and do not
@@ -298,6 +310,8 @@ class HotPathRunner:
             o = st.offsets[li][0]
             w_units = st.flat.detach()[o:o + lv.n_units * lv.unit_numel].view(lv.n_units, 4 * lv.cq, lv.cq, *lv.kernel_size)
             for kind in range(3):
+                if self.chain[li] and kind != _native.PREP_INVERSE:
+                    continue                        # the chain kernel stages the raw weights itself
                 side = self.side[k % self.N_SIDE]
                 if k < self.N_SIDE:
                     side.wait_event(fork)
@@ -374,11 +388,19 @@ class HotPathRunner:
     def _forward(self, s):
         self._per_level(lambda li, lv: self._forward_level(s, li, lv))
 
+    def _units_w(self, li):
+        lv, st = self.stack.levels[li], self.stack
+        o = st.offsets[li][0]
+        return st.flat.detach()[o:o + lv.n_units * lv.unit_numel].view(lv.n_units, 4 * lv.cq, lv.cq, *lv.kernel_size)
+
     def _forward_level(self, s, li, lv):
-        for u in range(lv.n_units):
-            flags = _native.FLAG_LOGDET_ACCUMULATE if u else 0
-            _native.forward(s.acts[li][u], flags=flags, out=s.acts[li][u + 1], logdet_out=s.logdet[li],
-                            **self._w(li, u, _native.PREP_FORWARD))
+        if self.chain[li]:
+            _native.chain(s.acts[li][0], self._units_w(li), s.acts_blk[li], logdet_out=s.logdet[li])
+        else:
+            for u in range(lv.n_units):
+                flags = _native.FLAG_LOGDET_ACCUMULATE if u else 0
+                _native.forward(s.acts[li][u], flags=flags, out=s.acts[li][u + 1], logdet_out=s.logdet[li],
+                                **self._w(li, u, _native.PREP_FORWARD))
         # logp and dz = d(-mean_n logp)/dz = z / (B * world)
         _native.gaussian_logp(s.acts[li][lv.n_units], s.logdet[li], 1.0 / (self.B * self.world),
                               logp_out=s.logp[li], dz_out=s.dzs[li][lv.n_units])
@@ -396,6 +418,9 @@ class HotPathRunner:
         def level(li, lv):
             main = torch.cuda.current_stream(self.device)
             k = base[li]
+            if self.chain[li] and lv.n_units > 1:   # the whole dX chain first (one launch), then every dW at once
+                _native.chain(s.dzs[li][lv.n_units], self._units_w(li), s.dzs_blk[li][:lv.n_units],
+                              units=range(lv.n_units - 1, 0, -1), transpose=True)
             ready = torch.cuda.Event()
             ready.record(main)                      # dzs[n] comes from the forward phase
             for u in reversed(range(lv.n_units)):
@@ -406,7 +431,7 @@ class HotPathRunner:
                                             out=st.unit_weight(li, u, self.grad), flags=_native.FLAG_QUARTER_GPU,
                                             workspace=self.workspaces[k % self.N_SIDE])
                 k += 1
-                if u > 0:
+                if u > 0 and not self.chain[li]:
                     _native.backward_input(s.dzs[li][u + 1], out=s.dzs[li][u],
                                            **self._w(li, u, _native.PREP_BACKWARD_INPUT))
                     ready = torch.cuda.Event()

@@ -56,6 +56,7 @@ extern "C" {
 #define FINC_FLAG_WAVE_SMEM 512u /* inverse: skip the register-window kernel, use the shared-memory wavefront kernel (testing) */
 #define FINC_FLAG_LOGDET_ACCUMULATE 8u /* forward: logdet[n] += ... (FlowSequential's `logdet += layer_logdet`) */
 #define FINC_FLAG_TF32_1PASS 1024u /* tensor-core entry points: single-pass TF32 products (PyTorch's default conv precision, ~5e-4) instead of the fp32-accurate 3xTF32 split */
+#define FINC_FLAG_CHAIN_TRANSPOSE 2048u /* finc_chain_f32: backward-data chain (transposed weights, opposite corner) */
 
 /* error codes (negative); positive return values are cudaError_t */
 #define FINC_OK 0
@@ -293,6 +294,24 @@ int finc_inverse_dense_prepare_f32(const float* w, void* prepared, void* scratch
                                    int G, int C, int H, int W, int kH, int kW, unsigned orders, void* stream);
 int finc_inverse_dense_f32(const float* z, const void* prepared, float* x, int B, int G, int C, int H, int W,
                            unsigned flags, void* stream);
+
+/* A chain of FInC units -- each optionally followed by its ActNorm o Conv1x1 affine map -- in ONE launch; the
+ * image tiles stay in shared memory between units.
+ *   cur = x;  for j in 0 .. n_units-1:  u = u_first + j*u_step;
+ *       cur = FInC(cur; w + u*w_stride)            (fastflow/fastflow.py:31-50, layers/conv.py:102-107; with
+ *                                                   FINC_FLAG_CHAIN_TRANSPOSE its backward-data map)
+ *       if A:  cur = (A + u*GC*GC) cur + (bias + u*GC)      (layers/actnorm.py:14-52 + layers/conv1x1.py:18-43,
+ *                                                   composed as for finc_affine1x1_f32; GC = G*C)
+ *       y + u*y_stride = cur                       (y_stride == 0: only the last unit's result is written to y)
+ *   logdet (nullable, [B]) = sum over the chain's units of H*W*sum log|diag| (affine terms are the caller's;
+ *   FINC_FLAG_LOGDET_ACCUMULATE adds into it).
+ * One launch replaces the FastFlowUnit + ActNorm + Conv1x1 sequence of a FastFlowStep (n_units = 1), or the
+ * n_units forward / backward-data launches of a stack of consecutive units.  Results are bit-identical to the
+ * per-unit calls.  kH = kW = 3, C in {1,2,3,6,12,24}; other shapes: FINC_E_UNSUPPORTED (finc_chain_supported = 0). */
+int finc_chain_supported(int G, int C, int H, int W, int kH, int kW, int with_affine);
+int finc_chain_f32(const float* x, const float* w, long w_stride, float* y, long y_stride, const float* A,
+                   const float* bias, float* logdet, int B, int G, int C, int H, int W, int kH, int kW,
+                   unsigned orders, int n_units, int u_first, int u_step, unsigned flags, void* stream);
 
 /* Debug aid, inactive unless the environment has FINC_DEBUG_TS=1: the tiled kernels then record
  * per-CTA %globaltimer marks (8 slots per CTA); this call synchronises the device and copies them. */

@@ -1,4 +1,5 @@
-"""phase times of the headline workload with / without level_parallel, results compared bit for bit (run under gpurun)"""
+"""phase times of the headline workload for the runner's execution options, results compared bit for bit
+(run under gpurun)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -7,10 +8,11 @@ from fincflow_b200.stack import FincStack, HotPathRunner
 
 dev = torch.device("cuda:0")
 res = {}
-for lp in (False, True):
+CASES = [("per-unit", dict(chain=False)), ("chain", dict(chain=True)), ("chain+level_parallel", dict(chain=True, level_parallel=True))]
+for name, kw in CASES:
     torch.manual_seed(0)
     stack = FincStack(bench.levels()).to(dev)
-    r = HotPathRunner(stack, 256, dev, slots=1, level_parallel=lp)
+    r = HotPathRunner(stack, 256, dev, slots=1, **kw)
     g = torch.Generator(device=dev).manual_seed(1)
     for li in range(len(stack.levels)):
         r.slots[0].acts[li][0].normal_(generator=g)
@@ -29,9 +31,11 @@ for lp in (False, True):
         ev[i][4].record()
     torch.cuda.synchronize()
     ph = [sum(ev[i][p].elapsed_time(ev[i][p + 1]) for i in range(K)) / K for p in range(4)]
-    print(f"level_parallel={lp}: " + ", ".join(f"{n} {v * 1e3:.1f} us" for n, v in zip(HotPathRunner.PHASES, ph)),
-          f"| step {ev[0][0].elapsed_time(ev[K - 1][4]) / K * 1e3:.1f} us")
-    res[lp] = (stack.flat.detach().clone(), [t.clone() for t in r.slots[0].logp], [r.slots[0].sample_out[k].clone() for k in sorted(r.slots[0].sample_out)])
-a, b = res[False], res[True]
-print("params equal:", torch.equal(a[0], b[0]), " logp equal:", all(torch.equal(x, y) for x, y in zip(a[1], b[1])),
-      " samples equal:", all(torch.equal(x, y) for x, y in zip(a[2], b[2])))
+    print(f"{name}: " + ", ".join(f"{n} {v * 1e3:.1f} us" for n, v in zip(HotPathRunner.PHASES, ph)),
+          f"| step {ev[0][0].elapsed_time(ev[K - 1][4]) / K * 1e3:.1f} us, launches/step {r.launches_per_step}")
+    res[name] = (stack.flat.detach().clone(), [t.clone() for t in r.slots[0].logp],
+                 [r.slots[0].sample_out[k].clone() for k in sorted(r.slots[0].sample_out)])
+a = res["per-unit"]
+for name, b in res.items():
+    print(name, "params equal:", torch.equal(a[0], b[0]), " logp equal:", all(torch.equal(x, y) for x, y in zip(a[1], b[1])),
+          " samples equal:", all(torch.equal(x, y) for x, y in zip(a[2], b[2])))

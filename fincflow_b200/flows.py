@@ -560,7 +560,28 @@ class FastFlowStep(_Chain):
             ("fastflow_unit", FastFlowUnit(size[0], size[0], kernel_size, mask_in_backward=True)),
             ("glow_unit", GlowStep(size, actnorm, width))]))
 
+    fused = True  # evaluation: FastFlowUnit + [ActNorm +] Conv1x1 as ONE finc_chain_f32 launch
+
     def forward(self, x):
+        unit, glow = self.fastflow_step.fastflow_unit, self.fastflow_step.glow_unit
+        act = getattr(glow.glow_step, "actnorm", None)
+        if (self.fused and glow.fused and not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32
+                and (act is None or act.is_initialized())
+                and _native.chain_supported(4, unit.cq, x.shape[2], x.shape[3], unit.kernel_size, True)):
+            # z = FInC(x) never leaves shared memory: y = A z + b is written, then the coupling layer
+            A, b, ld_pix, _, _ = _glue_constants(glow)
+            if b is None:   # no ActNorm: plain Conv1x1
+                b = getattr(self, "_zero_bias", None)
+                if b is None or b.device != x.device:
+                    b = self._zero_bias = torch.zeros(A.shape[0], device=x.device)
+            H, W = x.shape[2], x.shape[3]
+            y = _native.chain(x.contiguous(), unit.weight.detach().unsqueeze(0), torch.empty_like(x),
+                              A=A.unsqueeze(0), bias=b.unsqueeze(0))
+            y, ld = glow.glow_step.coupling(y)
+            ld = ld + (H * W) * ld_pix
+            if unit.logdet_mode == "tensor":   # otherwise the unit reports 0.0 like the reference (fastflow.py:34-50)
+                ld = ld + unit.logdet(x)
+            return y, ld
         return self._fwd(self.fastflow_step, x)
 
     def reverse(self, x):

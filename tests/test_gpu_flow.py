@@ -326,3 +326,33 @@ def test_flow_trainer_graph_step_equals_eager_step():
     assert np.allclose(l_e, l_g, rtol=1e-4)
     for a, b in zip(p_g, p_e):
         assert rel_err(a.cpu().numpy(), b.detach().cpu().numpy()) <= 1e-4
+
+
+@pytest.mark.parametrize("actnorm", [True, False])
+def test_fastflowstep_fused_eval_equals_layer_by_layer(actnorm):
+    """FastFlowStep under no_grad: FastFlowUnit + [ActNorm +] Conv1x1 in ONE finc_chain_f32 launch, then the
+    coupling layer -- same values and log-determinants as the three separate layers"""
+    from fincflow_b200 import _native, flows
+
+    torch.manual_seed(11)
+    for size, B in (((3, 32, 32), 64), ((6, 16, 16), 33), ((12, 8, 8), 256)):
+        step = flows.FastFlowStep((size[0] * 4, size[1] // 2, size[2] // 2), actnorm=actnorm, width=64).cuda()
+        x = torch.randn(B, size[0] * 4, size[1] // 2, size[2] // 2, device="cuda")
+        with torch.no_grad():
+            step(x)                                   # ActNorm data-dependent init (un-fused once)
+            for p in step.parameters():
+                p.add_(0.05 * torch.randn_like(p))
+            step(x)                                   # rebuilds the cached glue constants for the new parameters
+            n0 = _native.launch_count
+            y, ld = step(x)
+            fused_launches = _native.launch_count - n0
+            flows.FastFlowStep.fused = False
+            try:
+                n0 = _native.launch_count
+                y_ref, ld_ref = step(x)
+                ref_launches = _native.launch_count - n0
+            finally:
+                flows.FastFlowStep.fused = True
+        assert fused_launches == ref_launches - 1
+        assert rel_err(y.cpu().numpy(), y_ref.cpu().numpy()) <= 2e-6
+        assert rel_err(ld.cpu().numpy(), ld_ref.cpu().numpy()) <= 1e-6

@@ -273,7 +273,7 @@ static bool make_plan(const Shape& s, bool affine, Plan& p) {
     if (!(C == 1 || C == 2 || C == 3 || C == 6 || C == 12 || C == 24)) return false;
     // small output-channel blocks: a block of images is all the parallelism a CTA has, and at 4x4 / 8x8 tiles the
     // per-unit critical path (one warp's FMA chain), not the FMA count, sets the time
-    p.OB = C <= 3 ? C : (C <= 12 ? 2 : 4);
+    p.OB = C <= 3 ? C : (C == 6 ? 2 : (C == 12 ? 1 : 4));
     p.WT = s.W % 4 == 0 ? 4 : (s.W % 2 == 0 ? 2 : 1);
     p.nob = (C + p.OB - 1) / p.OB;
     p.nstrip = s.W / p.WT;
@@ -373,7 +373,7 @@ int finc_chain_f32(const float* x, const float* w, long w_stride, float* y, long
         case 2: return chain::launch_ct<2, 2>(a, p, grid, st);
         case 3: return chain::launch_ct<3, 3>(a, p, grid, st);
         case 6: return chain::launch_ct<6, 2>(a, p, grid, st);
-        case 12: return chain::launch_ct<12, 2>(a, p, grid, st);
+        case 12: return chain::launch_ct<12, 1>(a, p, grid, st);
         case 24: return chain::launch_ct<24, 4>(a, p, grid, st);
         default: return FINC_E_UNSUPPORTED;
     }

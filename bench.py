@@ -537,12 +537,15 @@ def main_ours(args):
     stack = FincStack(lvls).to(dev)
     NSLOT = 3
     runner = HotPathRunner(stack, B, dev, slots=NSLOT, process_group=pg)
+    chain_flags = list(runner.chain)
+    inv_chain_flags = None   # known after prepare()
     g = torch.Generator(device=dev).manual_seed(1000 + rank)  # different data per rank
     for s in runner.slots:
         for li in range(len(lvls)):
             s.acts[li][0].normal_(generator=g)
             s.zin[li].normal_(generator=g)
     runner.prepare()
+    inv_chain_flags = list(runner.inv_chain)
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -573,7 +576,7 @@ def main_ours(args):
     # ---- the same K steps with the sampling pass on its own stream (reported next to `value`) ------
     overlap = None
     if not args.no_overlap:
-        ov = HotPathRunner(stack, B, dev, slots=NSLOT, process_group=pg, overlap_sampling=True)
+        ov = HotPathRunner(stack, B, dev, slots=NSLOT, process_group=pg, overlap_sampling=True, level_parallel=True)
         for s_src, s_dst in zip(runner.slots, ov.slots):
             for li in range(len(lvls)):
                 s_dst.acts[li][0].copy_(s_src.acts[li][0])
@@ -596,9 +599,10 @@ def main_ours(args):
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
             ov_ms = float(t.item())
         overlap = {"value": round(B * world * K / (ov_ms * 1e-3), 1), "unit": "images/s", "ms_per_step": round(ov_ms / K, 4),
-                   "api": "HotPathRunner(overlap_sampling=True).step",
+                   "api": "HotPathRunner(overlap_sampling=True, level_parallel=True).step",
                    "note": "same K steps, but the sampling pass of step k runs on a second stream next to the forward / "
-                           "backward phases of step k+1 (both only read the weights of update k; update k+1 waits for it). "
+                           "backward phases of step k+1 (both only read the weights of update k; update k+1 waits for it), and the "
+                           "three levels of the stack -- independent inputs by construction -- run on one stream each inside a phase. "
                            "Not the headline: the timed region above keeps the phases serial so that per-phase and "
                            "per-launch durations stay clean"}
         del ov
@@ -662,12 +666,16 @@ def main_ours(args):
     # `avg_launch_us` is phase time / launches (an SM-time share, not a serial duration).
     n_units = sum(lv.n_units for lv in lvls)
     elems = sum(lv.n_units * B * lv.dim for lv in lvls)
+    n_chain = sum(chain_flags)                                  # levels whose forward / dX chains are ONE launch each
+    n_conv_fwd = sum(lv.n_units for lv, c in zip(lvls, chain_flags) if not c) + n_chain
+    n_conv_bwd = sum(lv.n_units - 1 for lv, c in zip(lvls, chain_flags) if not c) + n_chain
+    conv_name = "finc::chain::chain_kernel (all units of a level in one launch)" if n_chain else "finc::conv::conv_cta_kernel"
     phase_info = {
-        "forward_logdet": ("finc::conv::conv_cta_kernel (forward) + gaussian_logp", n_units + len(lvls),
+        "forward_logdet": (conv_name + " (forward) + gaussian_logp", n_conv_fwd + len(lvls),
                            8 * elems + sum(8 * B * lv.dim for lv in lvls)),
-        "backward": ("finc::conv::conv_cta_kernel (dX) + finc::wgrad_kernel (dW), overlapped", 2 * n_units - len(lvls),
-                     12 * elems),
-        "inverse": ("finc::rw::inverse_rw_kernel", n_units, 8 * elems),
+        "backward": (conv_name + " (dX) + finc::wgrad_kernel (dW), overlapped", n_conv_bwd + n_units, 12 * elems),
+        "inverse": ("finc::rw::inverse_rw_kernel" + (" (all units of a level in one launch, solved in place in shared memory)" if any(inv_chain_flags) else ""),
+                    sum(1 if c else lv.n_units for lv, c in zip(lvls, inv_chain_flags)), 8 * elems),
     }
     pm = dict(zip(HotPathRunner.PHASES, phase_ms))
     dom = max(phase_info, key=lambda p: pm[p])
@@ -716,7 +724,7 @@ def main_ours(args):
             "config_detail": {"parallelism": f"dp{world} (batch sharded; train step: " + ("fused NVLink peer-memory all-reduce + Adam kernel" if fused_flag else "NCCL all-reduce of the flat FInC gradient bucket") + "; sampling without collective)",
                        "l2": f"{NSLOT} rotating input/activation sets (~{NSLOT * 0.2:.1f} GB total, > 126 MB L2); "
                              "intermediates of a step stay L2-resident as in a real flow",
-                       "execution": "one CUDA graph per phase (forward, backward = dX chain with the dW launches fanned out over 6 side streams, optimizer, inverse); kernels launched with programmatic dependent launch"},
+                       "execution": "one CUDA graph per phase (forward: one chain launch per level -- all 16 units, tiles stay in shared memory, every activation still written; backward: one dX chain launch per level, then the 48 dW launches fanned out over 6 side streams; optimizer; inverse: one in-place chain launch per level); kernels launched with programmatic dependent launch"},
             "phases_ms": {k: round(v, 4) for k, v in pm.items()},
             "phase_images_per_s": {
                 "forward_logdet": round(B * world / (pm["forward_logdet"] * 1e-3)),

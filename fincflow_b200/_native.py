@@ -44,7 +44,7 @@ SYMBOLS = (
     "finc_tc_wgrad_workspace_bytes", "finc_tc_wgrad_f32", "finc_coupling_prepared_bytes", "finc_coupling_workspace_bytes", "finc_coupling_prepare_f32",
     "finc_coupling_apply_f32", "finc_coupling_backward_workspace_bytes", "finc_coupling_backward_f32",
     "finc_inverse_dense_bytes", "finc_inverse_dense_scratch_bytes", "finc_inverse_dense_prepare_f32",
-    "finc_inverse_dense_f32", "finc_chain_supported", "finc_chain_f32",
+    "finc_inverse_dense_f32", "finc_chain_supported", "finc_chain_f32", "finc_inverse_chain_f32",
 )
 
 _lib = None
@@ -128,6 +128,8 @@ def load():
     lib.finc_inverse_dense_prepare_f32.argtypes = [p, p, p, sz, i, i, i, i, i, i, u, p]
     lib.finc_inverse_dense_f32.restype = i
     lib.finc_inverse_dense_f32.argtypes = [p, p, p, i, i, i, i, i, u, p]
+    lib.finc_inverse_chain_f32.restype = i
+    lib.finc_inverse_chain_f32.argtypes = [p, p, ctypes.c_size_t, p, i, i, i, i, i, i, i, u, i, i, i, p]
     lib.finc_chain_supported.restype = i
     lib.finc_chain_supported.argtypes = [i, i, i, i, i, i, i]
     lib.finc_chain_f32.restype = i
@@ -656,6 +658,26 @@ def chain(x, w_units, out, G=4, orders=ORDERS_UNIT, A=None, bias=None, logdet_ou
                                  0 if logdet_out is None else logdet_out.data_ptr(), B, G, C, H, W, 3, 3, orders,
                                  n, units[0], step, flags, _stream(x)), "finc_chain_f32")
     return out
+
+
+def inverse_chain(z, tables, ksize, units, G=4, orders=ORDERS_UNIT, out=None):
+    """x = the inverse of the units `units` (an arithmetic sequence of rows of `tables`, applied in that order) in
+    ONE launch; `tables` = [U, nbytes] FINC_PREP_INVERSE tables from prepare_weights.  Raises FincNativeError
+    (rc FINC_E_UNSUPPORTED) when the shape is not covered -- callers fall back to one inverse() per unit."""
+    z = _prep(z, "z")
+    _bind_device(z)
+    units = list(units)
+    n = len(units)
+    step = units[1] - units[0] if n > 1 else 1
+    if (n > 1 and step == 0) or any(units[i + 1] - units[i] != step for i in range(n - 1)) or min(units) < 0 \
+            or max(units) >= tables.shape[0]:
+        raise FincNativeError("inverse_chain: `units` must be an arithmetic sequence of table rows")
+    B, CT, H, W = (int(v) for v in z.shape)
+    x = torch.empty_like(z) if out is None else out
+    _check(load().finc_inverse_chain_f32(z.data_ptr(), tables.data_ptr(), tables.stride(0) * tables.element_size(),
+                                         x.data_ptr(), B, G, CT // G, H, W, int(ksize[0]), int(ksize[1]), orders,
+                                         n, units[0], step, _stream(z)), "finc_inverse_chain_f32")
+    return x
 
 
 def sm_count() -> int:

@@ -184,6 +184,20 @@ int finc_inverse_f32(const float* z, const float* w, float* x, int B, int G, int
     return rc;
 }
 
+int finc_inverse_chain_f32(const float* z, const void* prepared, size_t prepared_stride_bytes, float* x, int B, int G,
+                           int C, int H, int W, int kH, int kW, unsigned orders, int n_units, int u_first, int u_step,
+                           void* stream) {
+    if (!shape_ok(B, G, C, H, W, kH, kW) || !prepared || n_units < 1 || prepared_stride_bytes % 16 != 0) return FINC_E_BADARG;
+    if (B == 0) return FINC_OK;
+    if (!z || !x) return FINC_E_BADARG;
+    const Shape s = mk(B, G, C, H, W, kH, kW, orders);
+    bool handled = false;
+    const int rc = launch_inverse_rw_chain(z, (const float*)prepared, x, s, true, n_units, u_first, u_step,
+                                           (long)(prepared_stride_bytes / 4), (cudaStream_t)stream, &handled);
+    if (rc) return rc;
+    return handled ? FINC_OK : FINC_E_UNSUPPORTED;
+}
+
 int finc_apply_grad_mask_f32(float* dw, int G, int C, int kH, int kW, unsigned orders, void* stream) {
     if (!shape_ok(1, G, C, 1, 1, kH, kW) || !dw) return FINC_E_BADARG;
     return launch_mask(dw, mk(1, G, C, 1, 1, kH, kW, orders), (cudaStream_t)stream);

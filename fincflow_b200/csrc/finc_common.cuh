@@ -184,6 +184,8 @@ int launch_inverse_wave(const float* z, const float* w, float* x, const Shape& s
                         bool* handled);
 int launch_inverse_rw(const float* z, const float* w, float* x, const Shape& s, bool prepared, cudaStream_t st,
                       bool* handled);
+int launch_inverse_rw_chain(const float* z, const float* w, float* x, const Shape& s, bool prepared, int n_units,
+                            int u_first, int u_step, long unit_stride, cudaStream_t st, bool* handled);
 bool rw_shape_supported(const Shape& s);
 size_t wave_prepared_floats(const Shape& s);
 int launch_wave_prepare(const float* w, float* out, int n_units, size_t w_stride, size_t out_stride, const Shape& s,

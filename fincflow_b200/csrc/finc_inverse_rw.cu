@@ -47,7 +47,14 @@ bool rw_shape_supported(const Shape& s) {
 // FINC_RW=0 disables the kernel (A/B runs against the shared-memory wavefront kernel)
 int launch_inverse_rw(const float* z, const float* w, float* x, const Shape& s, bool prepared, cudaStream_t st,
                       bool* handled) {
+    return launch_inverse_rw_chain(z, w, x, s, prepared, 1, 0, 1, 0, st, handled);
+}
+
+// n_units > 1: a chain of units solved in place in one launch (prepared tables, unit u at w + u * unit_stride)
+int launch_inverse_rw_chain(const float* z, const float* w, float* x, const Shape& s, bool prepared, int n_units,
+                            int u_first, int u_step, long unit_stride, cudaStream_t st, bool* handled) {
     *handled = false;
+    if (n_units > 1 && !prepared) return FINC_E_UNSUPPORTED;
     static const int enabled = env_int("FINC_RW", 1);
     if (!enabled) return 0;
     if (!((s.kH == 3 && s.kW == 3) || (s.kH == 5 && s.kW == 5))) return 0;
@@ -56,6 +63,7 @@ int launch_inverse_rw(const float* z, const float* w, float* x, const Shape& s, 
     const long tile_floats_l = (long)C * s.H * s.W;
     RwArgs a{};
     a.z = z; a.w = w; a.x = x; a.s = s; a.dbg = debug_ts_buffer(); a.prepared = prepared ? 1 : 0;
+    a.n_units = n_units; a.u_first = u_first; a.u_step = u_step; a.unit_stride = unit_stride;
     a.tile_floats = (int)tile_floats_l;
     a.tile_stride = (a.tile_floats + 3) & ~3;
     const int CPP = C <= 2 ? C : ((C + 3) / 4) * 4;
@@ -63,9 +71,9 @@ int launch_inverse_rw(const float* z, const float* w, float* x, const Shape& s, 
     const size_t wk_per_g = (size_t)s.kH * s.kW * tap_stride;
     const size_t smem_max = max_optin_smem_cached();
     const size_t budget = smem_max > 8192 ? smem_max - 4096 : 0;
-    if (wk_per_g * s.G * 4 <= budget / 2) { a.gsplit = 0; a.wk_floats = (int)(wk_per_g * s.G); }
-    else if (wk_per_g * 4 <= budget / 2) { a.gsplit = 1; a.wk_floats = (int)wk_per_g; }
-    else return 0;
+    if (wk_per_g * s.G * 4 * n_units <= budget / 2) { a.gsplit = 0; a.wk_floats = (int)(wk_per_g * s.G); }
+    else if (wk_per_g * 4 * n_units <= budget / 2) { a.gsplit = 1; a.wk_floats = (int)wk_per_g; }
+    else return n_units > 1 ? FINC_E_UNSUPPORTED : 0;
     a.bulk = (a.tile_floats % 4 == 0) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0) &&
              ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     if (prepared && (!a.bulk || (reinterpret_cast<uintptr_t>(w) & 15) != 0 || wave_prepared_floats(s) == 0))
@@ -111,7 +119,7 @@ int launch_inverse_rw(const float* z, const float* w, float* x, const Shape& s, 
     const int maxw_k = rw::rw_max_warps(C, KS, KS, P);
     const int maxw = env_int("FINC_RW_WARPS", maxw_k) < maxw_k ? env_int("FINC_RW_WARPS", maxw_k) : maxw_k;
 
-    const size_t wk_bytes = (size_t)((a.wk_floats + 31) & ~31) * 4;
+    const size_t wk_bytes = (size_t)((a.wk_floats + 31) & ~31) * 4 * n_units;
     const size_t avail = budget - wk_bytes;
     const int skew = NSTK > 1 ? 32 / NSTK : 0;   // stacks of a warp land on disjoint banks
     auto stage_bytes_of = [&](int T) { return (size_t)NSTK * ((size_t)T * a.tile_stride + skew) * 4; };

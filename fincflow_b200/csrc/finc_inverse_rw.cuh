@@ -51,6 +51,11 @@ struct RwArgs {
     int prepared;
     unsigned long long* dbg;
     long n_items;
+    // chain: n_units > 1 solves the units u_first, u_first + u_step, ... one after the other IN PLACE while the
+    // tiles stay in shared memory (prepared tables only; unit u's table at w + u * unit_stride floats); no
+    // intermediate result is ever written -- a sampling pass through consecutive units is one launch
+    int n_units, u_first, u_step;
+    long unit_stride;
 };
 
 template <int C, int KH, int KW, int P>
@@ -87,8 +92,9 @@ __global__ void __launch_bounds__(Cfg<C, KH, KW, P>::MAXW * 32, 1) inverse_rw_ke
     const int item_tiles = NSTK * a.T;
     const int stage_floats = NSTK * a.stack_stride;
     const int wk_pad = (a.wk_floats + 31) & ~31;
-    float* bufs = wk + wk_pad + (size_t)warp * a.S * stage_floats;
-    uint64_t* bar0 = reinterpret_cast<uint64_t*>(wk + wk_pad + (size_t)nwarps * a.S * stage_floats);
+    const int wk_all = wk_pad * a.n_units;
+    float* bufs = wk + wk_all + (size_t)warp * a.S * stage_floats;
+    uint64_t* bar0 = reinterpret_cast<uint64_t*>(wk + wk_all + (size_t)nwarps * a.S * stage_floats);
     uint64_t* bars = bar0 + warp * a.S;
     uint64_t* wbar = bar0 + nwarps * a.S;
 
@@ -119,10 +125,14 @@ __global__ void __launch_bounds__(Cfg<C, KH, KW, P>::MAXW * 32, 1) inverse_rw_ke
     else __syncwarp();
     pdl_wait();
     pdl_trigger();
-    if (a.prepared && threadIdx.x == 0) {  // the whole weight table: one bulk copy
+    if (a.prepared && threadIdx.x == 0) {  // the whole weight table of every unit of the chain: one bulk copy each
         const uint32_t wbytes = (uint32_t)a.wk_floats * 4;
-        mbar_arrive_expect_tx(wbar, wbytes);
-        bulk_g2s(wk, a.w + kPrepHeaderFloats + (a.gsplit ? (size_t)g_fixed * a.wk_floats : 0), wbytes, wbar);
+        mbar_arrive_expect_tx(wbar, wbytes * (uint32_t)a.n_units);
+        for (int uu = 0; uu < a.n_units; ++uu)
+            bulk_g2s(wk + (size_t)uu * wk_pad,
+                     a.w + (long)(a.u_first + uu * a.u_step) * a.unit_stride + kPrepHeaderFloats +
+                         (a.gsplit ? (size_t)g_fixed * a.wk_floats : 0),
+                     wbytes, wbar);
     }
     if (a.bulk) {
         for (int st = 0; st < a.S; ++st) {
@@ -183,7 +193,8 @@ __global__ void __launch_bounds__(Cfg<C, KH, KW, P>::MAXW * 32, 1) inverse_rw_ke
         }
         const int ord = order_of(s.orders, g);
         const bool bot = ord & 2, right = ord & 1;
-        const float* wg = wk + (size_t)(a.gsplit ? 0 : g) * KH * KW * TS;
+        for (int uu = 0; uu < a.n_units; ++uu) {   // the chain: every unit solves in place what the one before left
+        const float* wg = wk + (size_t)uu * wk_pad + (size_t)(a.gsplit ? 0 : g) * KH * KW * TS;
         const float* wgp = wg + p * CPP;  // rows of this lane's input channels: i = il*P + p
 
         // per-item register weights (negated: acc += x * (-w))
@@ -350,6 +361,8 @@ __global__ void __launch_bounds__(Cfg<C, KH, KW, P>::MAXW * 32, 1) inverse_rw_ke
                 for (int o = 0; o < C; ++o) zc[o] = zn[o];
             }
         }
+        if (a.n_units > 1) __syncwarp();   // the next unit reads what other lanes stored
+        }   // units of the chain
 
         if (threadIdx.x == 0 && k == 0) dbg_mark(a.dbg, 3);
         if (a.bulk) {

@@ -199,6 +199,8 @@ class HotPathRunner:
         # is covered; bit-identical to the per-unit launches
         self.chain = [chain and _native.chain_supported(4, lv.cq, lv.height, lv.width, lv.kernel_size)
                       for lv in stack.levels]
+        self.inv_chain = [False] * len(stack.levels)   # decided by _probe_inverse_chain() once the tables exist
+        self._want_inv_chain = chain
         # level_parallel: the levels of a FincStack have independent inputs, so their unit chains (forward,
         # dX, inverse) may run next to each other -- one stream per level, forked from and joined to the
         # current stream (inside a graph: parallel branches).  Batch-256 launches are latency-bound and do not
@@ -460,6 +462,13 @@ class HotPathRunner:
     def _inverse_level(self, s, li, lv):
         if self.device_latents:
             s.zin[li].normal_()
+        if self.inv_chain[li] and li not in self.dense:
+            # the whole sampling chain of the level: ONE launch, tiles stay in shared memory, no intermediate written
+            out = s.samp[li][(lv.n_units - 1) % 2]
+            _native.inverse_chain(s.zin[li], self.tables[li][_native.PREP_INVERSE], lv.kernel_size,
+                                  range(lv.n_units - 1, -1, -1), out=out)
+            s.sample_out[li] = out
+            return
         src, cur = s.zin[li], 0
         for u in reversed(range(lv.n_units)):
             if li in self.dense:
@@ -491,9 +500,27 @@ class HotPathRunner:
             self._prepare_weights()
             torch.cuda.synchronize(self.device)
 
+    def _probe_inverse_chain(self):
+        """which levels' sampling chains run as one finc_inverse_chain_f32 launch (register-window shapes whose
+        unit tables fit shared memory together); the others keep one launch per unit"""
+        self.inv_chain = [False] * len(self.stack.levels)
+        if not self._want_inv_chain or self.tables is None:
+            return
+        s = self.slots[0]
+        for li, lv in enumerate(self.stack.levels):
+            if lv.n_units < 2:
+                continue
+            try:
+                _native.inverse_chain(s.zin[li], self.tables[li][_native.PREP_INVERSE], lv.kernel_size,
+                                      range(lv.n_units - 1, -1, -1), out=s.samp[li][(lv.n_units - 1) % 2])
+                self.inv_chain[li] = True
+            except _native.FincNativeError:
+                pass
+
     def _prepare_warm_and_capture(self):
         self._prepare_weights()
         self.prepare_dense()
+        self._probe_inverse_chain()
         for s in self.slots:
             if self.host_io:
                 self._copy_in(s)

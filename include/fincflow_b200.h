@@ -308,6 +308,16 @@ int finc_inverse_dense_f32(const float* z, const void* prepared, float* x, int B
  * One launch replaces the FastFlowUnit + ActNorm + Conv1x1 sequence of a FastFlowStep (n_units = 1), or the
  * n_units forward / backward-data launches of a stack of consecutive units.  Results are bit-identical to the
  * per-unit calls.  kH = kW = 3, C in {1,2,3,6,12,24}; other shapes: FINC_E_UNSUPPORTED (finc_chain_supported = 0). */
+/* The sampling direction of a chain: x = FInC_u^-1(... ) for the units u_first, u_first + u_step, ... (n_units of
+ * them) solved IN PLACE by the register-window wavefront kernel while the tiles stay in shared memory: one launch,
+ * no intermediate result written (reference: one reverse_level2 call and (H+W-1)*Cq launches per unit,
+ * fastflow/fastflow.py:78-100).  `prepared` = FINC_PREP_INVERSE tables (finc_prepare_weights_f32), unit u's table at
+ * prepared + u * prepared_stride_bytes.  Bit-identical to n_units finc_inverse_f32 calls.  FINC_E_UNSUPPORTED when
+ * the shape is not covered by the register-window kernel or the tables of the chain do not fit shared memory. */
+int finc_inverse_chain_f32(const float* z, const void* prepared, size_t prepared_stride_bytes, float* x, int B, int G,
+                           int C, int H, int W, int kH, int kW, unsigned orders, int n_units, int u_first, int u_step,
+                           void* stream);
+
 int finc_chain_supported(int G, int C, int H, int W, int kH, int kW, int with_affine);
 int finc_chain_f32(const float* x, const float* w, long w_stride, float* y, long y_stride, const float* A,
                    const float* bias, float* logdet, int B, int G, int C, int H, int W, int kH, int kW,

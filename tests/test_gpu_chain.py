@@ -110,3 +110,35 @@ def test_chain_rejects_what_it_does_not_cover():
         _native.chain(x, w, torch.empty(2, 4, 12, 8, 8, device="cuda"), units=[0, 0])
     with pytest.raises(_native.FincNativeError):
         _native.chain(x, w, torch.empty(3, 4, 12, 8, 8, device="cuda"))
+
+
+@pytest.mark.parametrize("shape", [(256, 12, 16, 16, 16, 3), (256, 24, 8, 8, 16, 3), (256, 48, 4, 4, 16, 3), (37, 12, 16, 16, 3, 3),
+                                   (5, 48, 4, 4, 2, 3), (128, 4, 14, 14, 16, 3), (64, 12, 32, 32, 4, 3), (40, 12, 16, 16, 3, 5),
+                                   (1024, 12, 16, 16, 8, 3)])
+def test_inverse_chain_is_bit_identical_to_per_unit_launches(shape):
+    from fincflow_b200 import _native
+
+    B, C, H, W, U, k = shape
+    from fincflow_b200.fastflow import FastFlowUnit
+
+    torch.manual_seed(B + C + U)
+    w = torch.stack([FastFlowUnit(C, C, (k, k)).weight.detach() for _ in range(U)]).cuda().contiguous()
+    nb = _native.prepared_weights_bytes(_native.PREP_INVERSE, B, 4, C // 4, H, W, k, k)
+    assert nb > 0
+    tables = torch.empty((U, nb), dtype=torch.uint8, device="cuda")
+    _native.prepare_weights(w, tables, _native.PREP_INVERSE, B, H, W)
+    z = torch.randn(B, C, H, W, device="cuda")
+    x = _native.inverse_chain(z, tables, (k, k), range(U - 1, -1, -1))
+    cur = z
+    for u in reversed(range(U)):
+        cur = _native.inverse(cur, w[u])
+    assert torch.equal(x, cur)
+    # a sub-chain, ascending order
+    if U >= 3:
+        x2 = _native.inverse_chain(z, tables, (k, k), range(0, 2))
+        assert torch.equal(x2, _native.inverse(_native.inverse(z, w[0]), w[1]))
+    if B <= 40:
+        zz = x.cpu().numpy()
+        for u in range(U):
+            zz = fo.forward(zz, w[u].cpu().numpy())
+        assert np.abs(zz - z.cpu().numpy()).max() <= 1e-4

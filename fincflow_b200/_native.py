@@ -45,6 +45,7 @@ SYMBOLS = (
     "finc_coupling_apply_f32", "finc_coupling_backward_workspace_bytes", "finc_coupling_backward_f32",
     "finc_inverse_dense_bytes", "finc_inverse_dense_scratch_bytes", "finc_inverse_dense_prepare_f32",
     "finc_inverse_dense_f32", "finc_chain_supported", "finc_chain_f32", "finc_inverse_chain_f32",
+    "finc_backward_weight_batched_workspace_bytes", "finc_backward_weight_batched_f32",
 )
 
 _lib = None
@@ -128,6 +129,11 @@ def load():
     lib.finc_inverse_dense_prepare_f32.argtypes = [p, p, p, sz, i, i, i, i, i, i, u, p]
     lib.finc_inverse_dense_f32.restype = i
     lib.finc_inverse_dense_f32.argtypes = [p, p, p, i, i, i, i, i, u, p]
+    lib.finc_backward_weight_batched_workspace_bytes.restype = ctypes.c_size_t
+    lib.finc_backward_weight_batched_workspace_bytes.argtypes = [i, i, i, i, i, i, i, i]
+    lib.finc_backward_weight_batched_f32.restype = i
+    lib.finc_backward_weight_batched_f32.argtypes = [p, p, p, p, ctypes.c_size_t, i, i, i, i, i, i, i, u, u, i,
+                                                     ctypes.c_long, ctypes.c_long, ctypes.c_long, p]
     lib.finc_inverse_chain_f32.restype = i
     lib.finc_inverse_chain_f32.argtypes = [p, p, ctypes.c_size_t, p, i, i, i, i, i, i, i, u, i, i, i, p]
     lib.finc_chain_supported.restype = i
@@ -658,6 +664,35 @@ def chain(x, w_units, out, G=4, orders=ORDERS_UNIT, A=None, bias=None, logdet_ou
                                  0 if logdet_out is None else logdet_out.data_ptr(), B, G, C, H, W, 3, 3, orders,
                                  n, units[0], step, flags, _stream(x)), "finc_chain_f32")
     return out
+
+
+def backward_weight_batched_workspace_bytes(B, G, C, H, W, kH, kW, n_units) -> int:
+    return int(load().finc_backward_weight_batched_workspace_bytes(B, G, C, H, W, kH, kW, n_units))
+
+
+def backward_weight_batched(dz_units, x_units, out_units, ksize, G=4, orders=ORDERS_UNIT, flags=0, workspace=None):
+    """masked dW of U units in ONE launch: dz_units / x_units [U, B, G*C, H, W] (any uniform unit stride, each unit
+    contiguous), out_units [U, G*C, C, kH, kW] (uniform unit stride).  C ABI: finc_backward_weight_batched_f32."""
+    U, B, CT, H, W = (int(v) for v in dz_units.shape)
+    C = CT // G
+    for t in (dz_units, x_units):
+        if t.dtype != torch.float32 or not t[0].is_contiguous() or tuple(t.shape) != (U, B, CT, H, W):
+            raise FincNativeError("backward_weight_batched: [U, B, G*C, H, W] fp32 tensors with contiguous units expected")
+    if tuple(out_units.shape) != (U, CT, C, int(ksize[0]), int(ksize[1])) or not out_units[0].is_contiguous():
+        raise FincNativeError("backward_weight_batched: out must be [U, G*C, C, kH, kW] with contiguous units")
+    _bind_device(dz_units)
+    nbytes = int(load().finc_backward_weight_batched_workspace_bytes(B, G, C, H, W, int(ksize[0]), int(ksize[1]), U))
+    if nbytes == 0:
+        raise FincNativeError("backward_weight_batched: shape not covered", )
+    if workspace is None:
+        workspace = torch.zeros(nbytes, dtype=torch.uint8, device=dz_units.device)
+    _check(load().finc_backward_weight_batched_f32(dz_units.data_ptr(), x_units.data_ptr(), out_units.data_ptr(),
+                                                   workspace.data_ptr(), workspace.numel() * workspace.element_size(),
+                                                   B, G, C, H, W, int(ksize[0]), int(ksize[1]), orders, flags, U,
+                                                   dz_units.stride(0) if U > 1 else 0, x_units.stride(0) if U > 1 else 0,
+                                                   out_units.stride(0) if U > 1 else 0, _stream(dz_units)),
+           "finc_backward_weight_batched_f32")
+    return out_units
 
 
 def inverse_chain(z, tables, ksize, units, G=4, orders=ORDERS_UNIT, out=None):

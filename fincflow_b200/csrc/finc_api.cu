@@ -161,6 +161,25 @@ int finc_backward_weight_f32(const float* dz, const float* x, float* dw, void* w
     return rc;
 }
 
+size_t finc_backward_weight_batched_workspace_bytes(int B, int G, int C, int H, int W, int kH, int kW, int n_units) {
+    if (!shape_ok(B, G, C, H, W, kH, kW) || n_units < 1) return 0;
+    return wgrad_batched_workspace_floats(mk(B, G, C, H, W, kH, kW, 0), n_units) * (size_t)n_units * sizeof(float);
+}
+
+int finc_backward_weight_batched_f32(const float* dz, const float* x, float* dw, void* workspace, size_t workspace_bytes,
+                                     int B, int G, int C, int H, int W, int kH, int kW, unsigned orders, unsigned flags,
+                                     int n_units, long dz_unit_stride, long x_unit_stride, long dw_unit_stride,
+                                     void* stream) {
+    if (!shape_ok(B, G, C, H, W, kH, kW) || !dw || !dz || !x || n_units < 1 || B < 1) return FINC_E_BADARG;
+    if (!workspace) return FINC_E_WORKSPACE;
+    const Shape s = mk(B, G, C, H, W, kH, kW, orders);
+    bool handled = false;
+    const int rc = launch_wgrad_batched(dz, x, dw, (float*)workspace, workspace_bytes / sizeof(float), s, flags, n_units,
+                                        dz_unit_stride, x_unit_stride, dw_unit_stride, (cudaStream_t)stream, &handled);
+    if (rc) return rc;
+    return handled ? FINC_OK : FINC_E_UNSUPPORTED;
+}
+
 int finc_inverse_f32(const float* z, const float* w, float* x, int B, int G, int C, int H, int W, int kH, int kW,
                      unsigned orders, unsigned flags, void* stream) {
     if (!shape_ok(B, G, C, H, W, kH, kW) || !w) return FINC_E_BADARG;

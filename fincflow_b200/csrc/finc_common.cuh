@@ -194,6 +194,10 @@ constexpr int kPrepHeaderFloats = 32;  // 128-byte header in front of a prepared
 int launch_wgrad_fast(const float* dz, const float* x, float* dw, float* workspace, size_t ws_floats, const Shape& s,
                       unsigned flags, cudaStream_t st, bool* handled);
 size_t wgrad_workspace_floats(const Shape& s);
+size_t wgrad_batched_workspace_floats(const Shape& s, int n_units);
+int launch_wgrad_batched(const float* dz, const float* x, float* dw, float* workspace, size_t ws_floats, const Shape& s,
+                         unsigned flags, int n_units, long dz_ustride, long x_ustride, long dw_ustride,
+                         cudaStream_t st, bool* handled);
 
 int launch_conv_naive(const float* x, const float* w, float* y, const Shape& s, bool transpose, cudaStream_t st);
 int launch_inverse_naive(const float* z, const float* w, float* x, const Shape& s, cudaStream_t st);

@@ -53,6 +53,10 @@ struct WgArgs {
     int X, Z, nchunks;
     unsigned long long* dbg;
     unsigned m_nstrip, m_ch;
+    // batched over units (one launch for every unit of a level): blockIdx.z = unit * Z + slice; unit u reads
+    // dz + u * dz_ustride and x + u * x_ustride, writes dw + u * dw_ustride, reduces in workspace + u * ws_ustride
+    int n_units;
+    long dz_ustride, x_ustride, dw_ustride, ws_ustride;
 };
 
 __device__ __forceinline__ unsigned fastdiv(unsigned n, unsigned m) { return m ? __umulhi(n, m) : n; }
@@ -150,7 +154,12 @@ __global__ void __launch_bounds__((max_consumer_warps(OB, KH) + 1) * 32, 1) wgra
     uint64_t* empty = full + a.S;
     __shared__ int s_last;
 
-    const int g = blockIdx.y, zz = blockIdx.z;
+    const int g = blockIdx.y, uu = (int)blockIdx.z / a.Z, zz = (int)blockIdx.z - uu * a.Z;
+    const float* const dz_u = a.dz + (long)uu * a.dz_ustride;
+    const float* const x_u = a.x + (long)uu * a.x_ustride;
+    float* const dw_u = a.dw + (long)uu * a.dw_ustride;
+    float* const partial_u = a.partial + (long)uu * a.ws_ustride;
+    unsigned* const counters_u = a.counters + (long)uu * a.ws_ustride;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool is_producer = warp == (nthreads_c >> 5);
     const int ord = order_of(s.orders, g);
@@ -166,8 +175,8 @@ __global__ void __launch_bounds__((max_consumer_warps(OB, KH) + 1) * 32, 1) wgra
         float* ds = xs + half;
         for (int t = lane; t < nt; t += 32) {
             const long off = ((long)(n0 + t) * s.G + g) * a.tile_floats;
-            bulk_g2s(xs + t * a.tile_stride, a.x + off, (uint32_t)(a.tile_floats * 4), &full[st]);
-            bulk_g2s(ds + t * a.tile_stride, a.dz + off, (uint32_t)(a.tile_floats * 4), &full[st]);
+            bulk_g2s(xs + t * a.tile_stride, x_u + off, (uint32_t)(a.tile_floats * 4), &full[st]);
+            bulk_g2s(ds + t * a.tile_stride, dz_u + off, (uint32_t)(a.tile_floats * 4), &full[st]);
         }
     };
 
@@ -240,8 +249,8 @@ __global__ void __launch_bounds__((max_consumer_warps(OB, KH) + 1) * 32, 1) wgra
                 for (int tt = 0; tt < nt; ++tt) {
                     const long off = ((long)(n0 + tt) * s.G + g) * a.tile_floats;
                     for (int e = threadIdx.x; e < a.tile_floats; e += nthreads_c) {
-                        xs[tt * a.tile_stride + e] = a.x[off + e];
-                        ds[tt * a.tile_stride + e] = a.dz[off + e];
+                        xs[tt * a.tile_stride + e] = x_u[off + e];
+                        ds[tt * a.tile_stride + e] = dz_u[off + e];
                     }
                 }
                 asm volatile("bar.sync 1, %0;" ::"r"(nthreads_c) : "memory");
@@ -301,22 +310,22 @@ __global__ void __launch_bounds__((max_consumer_warps(OB, KH) + 1) * 32, 1) wgra
         const int ab = idx % (KH * KW);
         const long out = (((long)g * C + o) * C + i) * KH * KW + ab;
         if (!(a.flags & FINC_FLAG_NO_MASK) && ab == ca * KW + cbn && i >= o) v = 0.f;
-        if (a.flags & FINC_FLAG_ACCUMULATE) v += a.dw[out];
-        a.dw[out] = v;
+        if (a.flags & FINC_FLAG_ACCUMULATE) v += dw_u[out];
+        dw_u[out] = v;
     };
     for (int l = threadIdx.x; l < nloc; l += blockDim.x) {
         const int cl = l / NACC;
         float v = 0.f;
         for (int r = 0; r < segs_per_combo; ++r) v += red[(cl * segs_per_combo + r) * NACC + (l - cl * NACC)];
         if (direct) finish(l, v);
-        else a.partial[(long)blockIdx.x * xstride + slice + l] = v;
+        else partial_u[(long)blockIdx.x * xstride + slice + l] = v;
     }
     if (direct) return;
 
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned ticket = atomicAdd(&a.counters[g * a.Z + zz], 1u);
+        const unsigned ticket = atomicAdd(&counters_u[g * a.Z + zz], 1u);
         s_last = (ticket == (unsigned)(a.X - 1));
     }
     __syncthreads();
@@ -337,7 +346,7 @@ __global__ void __launch_bounds__((max_consumer_warps(OB, KH) + 1) * 32, 1) wgra
             const int l = l0 + tl;
             float v = 0.f;
             if (l < nloc && tl < (int)blockDim.x / parts) {
-                const float* pp = a.partial + slice + l;
+                const float* pp = partial_u + slice + l;
                 for (int xx0 = q; xx0 < a.X; xx0 += 8 * parts) {  // 8 independent loads in flight
                     float t8[8];
 #pragma unroll
@@ -363,7 +372,7 @@ __global__ void __launch_bounds__((max_consumer_warps(OB, KH) + 1) * 32, 1) wgra
             }
         }
     }
-    if (threadIdx.x == 0) a.counters[g * a.Z + zz] = 0u;  // leave the ticket clean
+    if (threadIdx.x == 0) counters_u[g * a.Z + zz] = 0u;  // leave the ticket clean
     __syncthreads();
     if (threadIdx.x == 0) dbg_mark(a.dbg, 5);
 }
@@ -520,13 +529,31 @@ size_t wgrad_workspace_floats(const Shape& s) {
     return kCounterBytes / 4 + f;
 }
 
+// workspace floats of ONE unit in a batched launch over n_units units (the units' regions are laid out back to back)
+size_t wgrad_batched_workspace_floats(const Shape& s, int n_units) {
+    Plan p{};
+    if (!make_plan(s, &p, n_units)) return 0;
+    return kCounterBytes / 4 + partial_floats(s, p);
+}
+
 int launch_wgrad_fast(const float* dz, const float* x, float* dw, float* workspace, size_t ws_floats, const Shape& s,
                       unsigned flags, cudaStream_t st, bool* handled) {
+    return launch_wgrad_batched(dz, x, dw, workspace, ws_floats, s, flags, 1, 0, 0, 0, st, handled);
+}
+
+// n_units > 1: every unit of a level in ONE launch (each gets 1/n_units of the SMs); unit u reads dz + u*dz_ustride,
+// x + u*x_ustride and writes dw + u*dw_ustride; the workspace holds n_units regions of
+// wgrad_batched_workspace_floats(s, n_units) floats
+int launch_wgrad_batched(const float* dz, const float* x, float* dw, float* workspace, size_t ws_floats, const Shape& s,
+                         unsigned flags, int n_units, long dz_ustride, long x_ustride, long dw_ustride,
+                         cudaStream_t st, bool* handled) {
     *handled = false;
     Plan p{};
     static const int quarter_div = getenv("FINC_WG_DIV") ? atoi(getenv("FINC_WG_DIV")) : 4;  // experiment knob
-    if (!make_plan(s, &p, (flags & FINC_FLAG_QUARTER_GPU) ? quarter_div : 1)) return 0;
-    if (ws_floats < kCounterBytes / 4 + partial_floats(s, p)) return FINC_E_WORKSPACE;
+    if (!make_plan(s, &p, n_units > 1 ? n_units : ((flags & FINC_FLAG_QUARTER_GPU) ? quarter_div : 1))) return 0;
+    const size_t ws_unit = kCounterBytes / 4 + partial_floats(s, p);
+    if (ws_floats < ws_unit * (size_t)n_units) return FINC_E_WORKSPACE;
+    if ((long)p.Z * n_units > 65535) return 0;
     {
         static const bool dbg_plan = getenv("FINC_WG_DEBUG") != nullptr;
         if (dbg_plan)
@@ -538,6 +565,8 @@ int launch_wgrad_fast(const float* dz, const float* x, float* dw, float* workspa
     a.dz = dz; a.x = x; a.dw = dw; a.s = s; a.flags = flags; a.dbg = debug_ts_buffer();
     a.counters = reinterpret_cast<unsigned*>(workspace);
     a.partial = workspace + kCounterBytes / 4;
+    a.n_units = n_units; a.dz_ustride = dz_ustride; a.x_ustride = x_ustride; a.dw_ustride = dw_ustride;
+    a.ws_ustride = (long)ws_unit;
     a.CH = p.CH; a.S = p.S; a.nob = p.nob; a.nstrip = p.nstrip; a.RR = p.RR; a.rpr = p.rpr;
     a.slots = p.slots; a.SP = p.SP; a.ncombo = p.ncombo; a.cpc = p.cpc; a.X = p.X; a.Z = p.Z; a.nchunks = p.nchunks;
     a.m_nstrip = magic(p.nstrip); a.m_ch = magic(p.CH);
@@ -546,10 +575,12 @@ int launch_wgrad_fast(const float* dz, const float* x, float* dw, float* workspa
     a.bulk = (a.tile_floats % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
              ((reinterpret_cast<uintptr_t>(dz) & 15) == 0);
     if (a.X > 1 && !(flags & FINC_FLAG_WORKSPACE_CLEAN)) {
-        cudaError_t e = cudaMemsetAsync(a.counters, 0, (size_t)s.G * a.Z * 4, st);
+        // the tickets of every unit (n_units = 1: just the first G*Z counters)
+        const size_t bytes = n_units > 1 ? ((size_t)(n_units - 1) * ws_unit + kCounterBytes / 4) * 4 : (size_t)s.G * a.Z * 4;
+        cudaError_t e = cudaMemsetAsync(a.counters, 0, bytes, st);
         if (e != cudaSuccess) return (int)e;
     }
-    dim3 grid(a.X, s.G, a.Z);
+    dim3 grid(a.X, s.G, a.Z * n_units);
     int rc;
     switch (p.OB) {
         case 1: rc = dispatch_wt<1>(p.WT, s.kH, a, grid, p.threads, p.smem, st); break;

@@ -192,13 +192,20 @@ class HotPathRunner:
 
     def __init__(self, stack: FincStack, batch: int, device, slots=1, lr=1e-3, host_io=False,
                  process_group=None, use_graphs=True, use_prepared=True, fused_collective=True,
-                 device_latents=False, overlap_sampling=False, dense_inverse=False, level_parallel=False, chain=True):
+                 device_latents=False, overlap_sampling=False, dense_inverse=False, level_parallel=False, chain=True,
+                 batched_wgrad=True):
         self.stack, self.B, self.device = stack, batch, torch.device(device)
         # chain: the forward pass of a level and its backward-data chain are ONE launch each (finc_chain_f32: the
         # image tiles stay in shared memory between units; all activations are still written) wherever the shape
         # is covered; bit-identical to the per-unit launches
         self.chain = [chain and _native.chain_supported(4, lv.cq, lv.height, lv.width, lv.kernel_size)
                       for lv in stack.levels]
+        # dW of all units of a chained level in one launch (finc_backward_weight_batched_f32): own workspace per level
+        self.wg_batched = []
+        for lv, c in zip(stack.levels, self.chain):
+            nb = _native.backward_weight_batched_workspace_bytes(batch, 4, lv.cq, lv.height, lv.width, *lv.kernel_size,
+                                                                 lv.n_units - 1) if (c and batched_wgrad and lv.n_units > 2) else 0
+            self.wg_batched.append(torch.zeros(nb, dtype=torch.uint8, device=self.device) if nb else None)
         self.inv_chain = [False] * len(stack.levels)   # decided by _probe_inverse_chain() once the tables exist
         self._want_inv_chain = chain
         # level_parallel: the levels of a FincStack have independent inputs, so their unit chains (forward,
@@ -413,6 +420,7 @@ class HotPathRunner:
         dzs[u] = dL/d acts[u]; the data gradient of unit 0 is never needed."""
         st = self.stack
         outer = torch.cuda.current_stream(self.device)
+        used = set()                                # side streams that got work (only those can be joined)
         base = [0]
         for lv in st.levels:
             base.append(base[-1] + lv.n_units)
@@ -423,10 +431,30 @@ class HotPathRunner:
             if self.chain[li] and lv.n_units > 1:   # the whole dX chain first (one launch), then every dW at once
                 _native.chain(s.dzs[li][lv.n_units], self._units_w(li), s.dzs_blk[li][:lv.n_units],
                               units=range(lv.n_units - 1, 0, -1), transpose=True)
+                if self.wg_batched[li] is not None:
+                    # dW of the units 1 .. U-1 in ONE launch (their x are slices of one tensor), unit 0 (x = the
+                    # level's input) in a second one, on two side streams
+                    U, o = lv.n_units, self.stack.offsets[li][0]
+                    gw = self.grad[o:o + U * lv.unit_numel].view(U, 4 * lv.cq, lv.cq, *lv.kernel_size)
+                    ready = torch.cuda.Event()
+                    ready.record(main)
+                    used.update(((2 * li) % self.N_SIDE, (2 * li + 1) % self.N_SIDE))
+                    side = self.side[(2 * li) % self.N_SIDE]
+                    side.wait_event(ready)
+                    with torch.cuda.stream(side):
+                        _native.backward_weight_batched(s.dzs_blk[li][2:U + 1], s.acts_blk[li][:U - 1], gw[1:],
+                                                        lv.kernel_size, workspace=self.wg_batched[li])
+                    side = self.side[(2 * li + 1) % self.N_SIDE]
+                    side.wait_event(ready)
+                    with torch.cuda.stream(side):
+                        _native.backward_weight(s.dzs[li][1], s.acts[li][0], lv.kernel_size, out=gw[0],
+                                                flags=_native.FLAG_QUARTER_GPU, workspace=self.workspaces[(2 * li + 1) % self.N_SIDE])
+                    return
             ready = torch.cuda.Event()
             ready.record(main)                      # dzs[n] comes from the forward phase
             for u in reversed(range(lv.n_units)):
                 side = self.side[k % self.N_SIDE]
+                used.add(k % self.N_SIDE)
                 side.wait_event(ready)
                 with torch.cuda.stream(side):
                     _native.backward_weight(s.dzs[li][u + 1], s.acts[li][u], lv.kernel_size,
@@ -440,8 +468,8 @@ class HotPathRunner:
                     ready.record(main)
 
         self._per_level(level)
-        for side in self.side[:min(base[-1], self.N_SIDE)]:   # only the streams that got work (a stream outside the capture cannot be joined)
-            outer.wait_stream(side)
+        for i in sorted(used):
+            outer.wait_stream(self.side[i])
 
     def _optimizer(self, s):
         if self.fused_collective:

@@ -308,6 +308,17 @@ int finc_inverse_dense_f32(const float* z, const void* prepared, float* x, int B
  * One launch replaces the FastFlowUnit + ActNorm + Conv1x1 sequence of a FastFlowStep (n_units = 1), or the
  * n_units forward / backward-data launches of a stack of consecutive units.  Results are bit-identical to the
  * per-unit calls.  kH = kW = 3, C in {1,2,3,6,12,24}; other shapes: FINC_E_UNSUPPORTED (finc_chain_supported = 0). */
+/* finc_backward_weight_f32 for n_units units in ONE launch (each unit gets 1/n_units of the SMs): unit u reads
+ * dz + u*dz_unit_stride and x + u*x_unit_stride (floats) and writes dw + u*dw_unit_stride -- e.g. every unit of a
+ * level once its backward-data chain has produced all dz (the reference: one cuDNN wgrad + `grad * mask` per
+ * layer, layers/conv.py:98-99).  Same masked, deterministic result as the per-unit call.  FINC_E_UNSUPPORTED when
+ * the tiled kernel does not cover the shape (call finc_backward_weight_f32 per unit then). */
+size_t finc_backward_weight_batched_workspace_bytes(int B, int G, int C, int H, int W, int kH, int kW, int n_units);
+int finc_backward_weight_batched_f32(const float* dz, const float* x, float* dw, void* workspace, size_t workspace_bytes,
+                                     int B, int G, int C, int H, int W, int kH, int kW, unsigned orders, unsigned flags,
+                                     int n_units, long dz_unit_stride, long x_unit_stride, long dw_unit_stride,
+                                     void* stream);
+
 /* The sampling direction of a chain: x = FInC_u^-1(... ) for the units u_first, u_first + u_step, ... (n_units of
  * them) solved IN PLACE by the register-window wavefront kernel while the tiles stay in shared memory: one launch,
  * no intermediate result written (reference: one reverse_level2 call and (H+W-1)*Cq launches per unit,

@@ -142,3 +142,29 @@ def test_inverse_chain_is_bit_identical_to_per_unit_launches(shape):
         for u in range(U):
             zz = fo.forward(zz, w[u].cpu().numpy())
         assert np.abs(zz - z.cpu().numpy()).max() <= 1e-4
+
+
+@pytest.mark.parametrize("shape", [(256, 12, 16, 16, 15, 3), (256, 24, 8, 8, 15, 3), (256, 48, 4, 4, 15, 3), (37, 12, 16, 16, 3, 3),
+                                   (128, 4, 14, 14, 16, 3), (64, 12, 32, 32, 4, 3), (40, 12, 16, 16, 2, 5), (5, 48, 4, 4, 1, 3)])
+def test_batched_weight_gradient_equals_per_unit_launches(shape):
+    from fincflow_b200 import _native
+
+    B, C, H, W, U, k = shape
+    torch.manual_seed(B * U + C)
+    dz = torch.randn(U + 1, B, C, H, W, device="cuda")
+    x = torch.randn(U + 1, B, C, H, W, device="cuda")
+    out = torch.full((U, C, C // 4, k, k), float("nan"), device="cuda")
+    # unit u reads dz[u + 1] and x[u]: the slices the trainer passes
+    _native.backward_weight_batched(dz[1:], x[:U], out, (k, k))
+    for u in range(U):
+        want = _native.backward_weight(dz[u + 1], x[u], (k, k))
+        assert rel_err(out[u].cpu().numpy(), want.cpu().numpy()) <= 2e-6, f"unit {u}"
+        assert torch.equal(out[u] == 0, want == 0)               # the same masked entries
+    if B <= 40:
+        ref = fo.backward_weight(dz[1].cpu().numpy(), x[0].cpu().numpy(), (k, k))
+        assert rel_err(out[0].cpu().numpy(), ref) <= REL_TOL
+    # twice on the same workspace (tickets must be left clean)
+    ws = torch.zeros(_native.backward_weight_batched_workspace_bytes(B, 4, C // 4, H, W, k, k, U), dtype=torch.uint8, device="cuda")
+    a = _native.backward_weight_batched(dz[1:], x[:U], torch.empty_like(out), (k, k), workspace=ws)
+    b = _native.backward_weight_batched(dz[1:], x[:U], torch.empty_like(out), (k, k), workspace=ws)
+    assert torch.equal(a, b) and torch.equal(a, out)

@@ -37,5 +37,7 @@ for name, kw in CASES:
                  [r.slots[0].sample_out[k].clone() for k in sorted(r.slots[0].sample_out)])
 a = res["per-unit"]
 for name, b in res.items():
-    print(name, "params equal:", torch.equal(a[0], b[0]), " logp equal:", all(torch.equal(x, y) for x, y in zip(a[1], b[1])),
-          " samples equal:", all(torch.equal(x, y) for x, y in zip(a[2], b[2])))
+    rel = lambda x, y: float((x - y).abs().max() / y.abs().max())
+    print(name, "vs per-unit: params rel", f"{rel(b[0], a[0]):.1e}", " logp rel", f"{max(rel(x, y) for x, y in zip(b[1], a[1])):.1e}",
+          " samples rel", f"{max(rel(x, y) for x, y in zip(b[2], a[2])):.1e}",
+          "(chains are bit-identical; the batched dW sums its batch slices in another fixed order)")

@@ -724,7 +724,7 @@ def main_ours(args):
             "config_detail": {"parallelism": f"dp{world} (batch sharded; train step: " + ("fused NVLink peer-memory all-reduce + Adam kernel" if fused_flag else "NCCL all-reduce of the flat FInC gradient bucket") + "; sampling without collective)",
                        "l2": f"{NSLOT} rotating input/activation sets (~{NSLOT * 0.2:.1f} GB total, > 126 MB L2); "
                              "intermediates of a step stay L2-resident as in a real flow",
-                       "execution": "one CUDA graph per phase (forward: one chain launch per level -- all 16 units, tiles stay in shared memory, every activation still written; backward: one dX chain launch per level, then the 48 dW launches fanned out over 6 side streams; optimizer; inverse: one in-place chain launch per level); kernels launched with programmatic dependent launch"},
+                       "execution": "one CUDA graph per phase (forward: one chain launch per level -- all 16 units, tiles stay in shared memory, every activation still written; backward: one dX chain launch per level, then two dW launches per level -- units 1-15 batched, unit 0 -- on side streams; optimizer; inverse: one in-place chain launch per level); kernels launched with programmatic dependent launch"},
             "phases_ms": {k: round(v, 4) for k, v in pm.items()},
             "phase_images_per_s": {
                 "forward_logdet": round(B * world / (pm["forward_logdet"] * 1e-3)),

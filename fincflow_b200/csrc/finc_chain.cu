@@ -22,6 +22,7 @@
 // it every branch of conv_sub) is warp-uniform.  The accumulation order of an output element (input channel,
 // kernel row, kernel column) is the one of conv_cta_kernel: results are bit-identical to the per-unit launches.
 #include <algorithm>
+#include <cstdlib>
 
 #include "finc_conv.cuh"
 
@@ -303,6 +304,10 @@ static bool make_plan(const Shape& s, bool affine, Plan& p) {
         if (score > best + 1e-9) { best = score; best_ipb = ipb; }
     }
     if (best_ipb == 0) return false;
+    if (const char* e = getenv("FINC_CHAIN_IPB")) {   // experiment knob
+        const int v = atoi(e);
+        if (v >= 1 && v <= s.B && smem_for(v) <= max_smem) best_ipb = v;
+    }
     p.IPB = best_ipb;
     const int nsub = p.IPB * sub_per_tile;
     p.seg = nsub >= 128 ? 128 : (nsub + 31) / 32 * 32;

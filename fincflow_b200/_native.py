@@ -179,10 +179,12 @@ def _prep(t: torch.Tensor, name: str) -> torch.Tensor:
 
 
 def _bind_device(t: torch.Tensor):
+    """make the tensor's device the current CUDA device of this thread.  Checked against the runtime on every call
+    (torch.cuda.current_device() is a cudaGetDevice): a cached value goes stale when torch switches devices
+    (torch.cuda.set_device, leaving a `with torch.cuda.device(i)` block)."""
     dev = t.device.index
-    if getattr(_tls, "device", None) != dev:
+    if torch.cuda.current_device() != dev:
         _check(load().finc_set_device(dev), "finc_set_device", 0)
-        _tls.device = dev
 
 
 def _stream(t: torch.Tensor) -> int:

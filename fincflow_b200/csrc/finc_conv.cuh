@@ -246,6 +246,8 @@ __device__ __forceinline__ void conv_sub(const float* __restrict__ xt, const flo
     }
 }
 
+__device__ __forceinline__ int nob_check(int nob_arg, int ct, int ob) { return ct > 0 ? (ct + ob - 1) / ob : nob_arg; }
+
 template <int CT, int OB, int WT, int KH, int KW, int RB = 1>
 __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kernel(const ConvArgs a) {
     constexpr int OBP = ObPad<OB>::value;
@@ -293,6 +295,11 @@ __global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1) conv_cta_kern
     pdl_trigger();  // successor may start its own prologue
     if (a.bulk && is_producer) {
         if (a.prepared && lane == 0) {  // the whole weight table: one bulk copy
+            // a table is only valid for the plan it was prepared for (kind, output block, blocks): refuse others
+            if (blockIdx.x == 0 && blockIdx.y == 0 &&
+                (__ldg(a.w) != 1179208259.f || (int)__ldg(a.w + 1) != a.transpose || (int)__ldg(a.w + 2) != OB ||
+                 (int)__ldg(a.w + 3) != nob_check(a.nob, CT, OB)))
+                __trap();
             const uint32_t wbytes = (uint32_t)a.wk_floats * 4;
             mbar_arrive_expect_tx(wbar, wbytes);
             bulk_g2s(wk, a.w + kPrepHeaderFloats + (a.gsplit ? (size_t)g_fixed * a.wk_floats : 0), wbytes, wbar);

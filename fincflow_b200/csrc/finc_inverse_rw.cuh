@@ -126,6 +126,10 @@ __global__ void __launch_bounds__(Cfg<C, KH, KW, P>::MAXW * 32, 1) inverse_rw_ke
     pdl_wait();
     pdl_trigger();
     if (a.prepared && threadIdx.x == 0) {  // the whole weight table of every unit of the chain: one bulk copy each
+        if (blockIdx.x == 0 && blockIdx.y == 0) {   // refuse a table of another kind / layout
+            const float* h = a.w + (long)a.u_first * a.unit_stride;
+            if (__ldg(h) != 1179208259.f || (int)__ldg(h + 1) != 2 || (int)__ldg(h + 2) != CPP || (int)__ldg(h + 3) != TS) __trap();
+        }
         const uint32_t wbytes = (uint32_t)a.wk_floats * 4;
         mbar_arrive_expect_tx(wbar, wbytes * (uint32_t)a.n_units);
         for (int uu = 0; uu < a.n_units; ++uu)

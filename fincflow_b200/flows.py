@@ -554,10 +554,13 @@ def _fused_glow_reverse(self, z):
 
 
 class FastFlowStep(_Chain):
-    def __init__(self, size, actnorm=False, kernel_size=(3, 3), width=512):
+    def __init__(self, size, actnorm=False, kernel_size=(3, 3), width=512, mask_in_backward=True):
         super().__init__()
+        # mask_in_backward=True applies the FInC gradient mask inside the weight-gradient kernel.  The reference clips
+        # the gradient norm over the UNMASKED gradients and masks afterwards (train/experiment.py:243-250): pass
+        # False (and call clear_grad / reset_gradients after clipping) when that ordering matters.
         self.fastflow_step = nn.Sequential(OrderedDict([
-            ("fastflow_unit", FastFlowUnit(size[0], size[0], kernel_size, mask_in_backward=True)),
+            ("fastflow_unit", FastFlowUnit(size[0], size[0], kernel_size, mask_in_backward=mask_in_backward)),
             ("glow_unit", GlowStep(size, actnorm, width))]))
 
     fused = True  # evaluation: FastFlowUnit + [ActNorm +] Conv1x1 as ONE finc_chain_f32 launch
@@ -589,11 +592,12 @@ class FastFlowStep(_Chain):
 
 
 class FastFlowLevel(nn.Module):
-    def __init__(self, size, block_size=16, actnorm=False, kernel_size=(3, 3), width=512):
+    def __init__(self, size, block_size=16, actnorm=False, kernel_size=(3, 3), width=512, mask_in_backward=True):
         super().__init__()
         size = (size[0] * 4, size[1] // 2, size[2] // 2)
         self.fastflow_level = nn.ModuleList([Squeeze(),
-                                             *[FastFlowStep(size, actnorm, kernel_size, width) for _ in range(block_size)],
+                                             *[FastFlowStep(size, actnorm, kernel_size, width, mask_in_backward)
+                                               for _ in range(block_size)],
                                              SplitPrior(size, width)])
 
     def forward(self, x):
@@ -618,17 +622,18 @@ class FastFlow(nn.Module):
     scripts); the MNIST and ImageNet64 scripts use ONE final step (`final_steps=1`)."""
 
     def __init__(self, n_blocks=2, block_size=16, image_size=(1, 28, 28), actnorm=False, kernel_size=(3, 3),
-                 final_steps=None, width=512):
+                 final_steps=None, width=512, mask_in_backward=True):
         super().__init__()
         C_in, H, W = image_size
         self.output_size = (C_in * 2 ** (n_blocks + 1), H // 2 ** n_blocks, W // 2 ** n_blocks)
         self.preprocess = Preprocess(image_size)
         self.fastflow_levels = nn.ModuleList([
-            FastFlowLevel((C_in * 2 ** i, H // 2 ** i, W // 2 ** i), block_size, actnorm, kernel_size, width)
+            FastFlowLevel((C_in * 2 ** i, H // 2 ** i, W // 2 ** i), block_size, actnorm, kernel_size, width,
+                          mask_in_backward)
             for i in range(n_blocks - 1)])
         self.squeeze = Squeeze()
         n_final = block_size if final_steps is None else final_steps
-        self.fastflow_step = nn.Sequential(*[FastFlowStep(self.output_size, actnorm, kernel_size, width)
+        self.fastflow_step = nn.Sequential(*[FastFlowStep(self.output_size, actnorm, kernel_size, width, mask_in_backward)
                                              for _ in range(n_final)])
         self.base_distribution = GaussianPrior(self.output_size)
 
@@ -674,6 +679,9 @@ class FastFlow(nn.Module):
         return self.preprocess.reverse(x)
 
     def log_prob(self, x, bits_per_pixel=False):
+        """bits_per_pixel: per IMAGE dimension (x[0].numel()).  The reference divides by `zs[0].numel()`, a
+        batch-sized latent tensor (fastflow_cifar_multi_gpu.py log_prob), so its printed value scales with the batch
+        size and is not comparable; its training metric (train/experiment.py:279-295) agrees with this one."""
         zs, logp = self.forward(x)
         return logp / (math.log(2) * x[0].numel()) if bits_per_pixel else logp
 

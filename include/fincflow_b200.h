@@ -211,8 +211,9 @@ int finc_affine1x1_backward_weight_f32(const float* dy, const float* x, float* d
  *     is not covered by the tiled kernels (then FINC_FLAG_PREPARED must not be used).
  *   finc_prepare_weights_f32: builds `n_units` tables in one launch; unit u reads
  *     w + u*w_stride_floats and writes prepared + u*prepared_stride_bytes.
- * A table is valid for exactly the (kind, B, G, C, H, W, kH, kW, orders) it was prepared for and
- * until the weights change.  Pass it as `w` together with FINC_FLAG_PREPARED (the forward table
+ * A table is valid for exactly the (kind, B, G, C, H, W, kH, kW, orders) it was prepared for -- the SAME batch size
+ * B included: the forward / backward-input layout depends on the launch plan chosen for B -- and until the weights
+ * change.  The kernels check the table header (magic, kind, layout parameters) and trap on a mismatch.  Pass it as `w` together with FINC_FLAG_PREPARED (the forward table
  * carries the unit's logdet, so `logdet` output keeps working). */
 #define FINC_PREP_FORWARD 0
 #define FINC_PREP_BACKWARD_INPUT 1

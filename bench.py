@@ -426,6 +426,49 @@ def kernel_detail(torch, _native, dev, peak):
     return out
 
 
+def tensor_roofline(torch, dev):
+    """the Coupling network's GEMMs (tcgen05 3xTF32, igemm_kernel) alone: TFLOP/s of TF32 MMAs issued (3 per fp32
+    product) against the tensor-core peak.  kind::tf32 runs at half the bf16 rate, so peak = MEASURED_PEAKS.json's
+    cuBLAS bf16 figure / 2 (burst for single launches; the sustained one for back-to-back phases: both kinds of run
+    sit at the 1000 W power cap)."""
+    from fincflow_b200 import _native
+
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            mp = json.load(f)
+        peak_burst, peak_sust, src = mp["bf16_tflops"] / 2, mp.get("bf16_tflops_sustained", mp["bf16_tflops"]) / 2, \
+            "measured (MEASURED_PEAKS.json bf16_tflops / 2: kind::tf32 MMAs run at half the bf16 rate)"
+    except Exception:
+        peak_burst = peak_sust = 2250.0 / 2
+        src = "fallback (B200_PROFILING.md: 2.25 PFLOP/s dense bf16, / 2 for tf32)"
+    res = []
+    for taps, name in ((1, "1x1 512->512 (coupling conv2)"), (9, "3x3 512->512 (long-K case)")):
+        Bc, H, W, Cin, N = PER_GPU_BATCH, 16, 16, 512, 512
+        k = 3 if taps == 9 else 1
+        x = torch.randn(Bc, H, W, Cin, device=dev)
+        w = torch.randn(N, Cin, k, k, device=dev) / (Cin * taps) ** 0.5
+        wp = _native.tc_conv_prepare_weights(w, 0)
+        bias = torch.zeros(N, device=dev)
+        y = _native.tc_conv_nhwc(x, wp, bias, N, taps, relu=True)
+        for _ in range(3):
+            _native.tc_conv_nhwc(x, wp, bias, N, taps, relu=True, out=y)
+        torch.cuda.synchronize(dev)
+        n = 10 if taps == 1 else 4
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            _native.tc_conv_nhwc(x, wp, bias, N, taps, relu=True, out=y)
+        e1.record()
+        e1.synchronize()
+        us = e0.elapsed_time(e1) / n * 1e3
+        mma_tflops = 3 * 2.0 * Bc * H * W * Cin * taps * N / us / 1e6
+        res.append({"gemm": name, "pixels": Bc * H * W, "us": round(us, 1), "fp32_equivalent_tflops": round(mma_tflops / 3, 1),
+                    "achieved": round(mma_tflops, 1), "frac": round(mma_tflops / peak_burst, 3)})
+        del x, y, w, wp
+    return {"bound": "tensor", "unit": "TFLOP/s of TF32 MMAs (3 per fp32-accurate product)", "peak": round(peak_burst, 1),
+            "peak_sustained": round(peak_sust, 1), "peak_source": src, "kernel": "finc::tc::igemm_kernel<128, 3, ...>", "gemms": res}
+
+
 def whole_flow_detail(torch, dev, world=1, rank=0, pg=None):
     """cfg3_full_flow: the COMPLETE CIFAR-10-shaped FInCFlow (3 blocks x 16 steps, coupling width 512) with every
     layer on our kernels -- FInC units, fused ActNorm+Conv1x1, tensor-core Coupling (3xTF32, fp32 parity), fused
@@ -497,6 +540,10 @@ def whole_flow_detail(torch, dev, world=1, rank=0, pg=None):
         m.train()
     except Exception as e:
         out["graph_error"] = repr(e)
+    try:   # the GEMM the step is made of, against the measured tensor-core peak
+        out["tensor_roofline"] = tensor_roofline(torch, dev)
+    except Exception as e:
+        out["tensor_roofline"] = {"error": repr(e)}
     out["replica_param_maxdiff"] = trainer.replica_max_diff()
     trainer.close()   # the step graph holds NCCL work: it must go before the process group does
     out["round1_same_model_pytorch_glue"] = {"train_step_ms": 90.9, "sample_ms": 35.1,

@@ -127,7 +127,7 @@ def run_extra_workloads(torch, dev, world, rank, pg, K, names=None):
             out.append({"name": name, "what": spec["what"], "per_gpu_batch": B, "global_batch": gb,
                         "scaling": spec["scaling"], "steps": K, "ms_per_step": round(tot, 4),
                         "phases_ms": {k: round(v, 4) for k, v in pm.items()}, "images_per_s": ips,
-                        "dense_inverse_levels": sorted(runner.dense),
+                        "dense_inverse_levels": sorted(runner.dense), "inverse_chain_units_per_launch": list(runner.inv_chain),
                         "frac_of_hbm_peak": {k: round(8 * elems * (1.5 if k == "backward" else 1.0) / (v * 1e-3) / 1e9 / peak, 4)
                                              for k, v in pm.items() if k != "optimizer"}})
             del runner, stack
@@ -722,7 +722,7 @@ def main_ours(args):
                            8 * elems + sum(8 * B * lv.dim for lv in lvls)),
         "backward": (conv_name + " (dX) + finc::wgrad_kernel (dW), overlapped", n_conv_bwd + n_units, 12 * elems),
         "inverse": ("finc::rw::inverse_rw_kernel" + (" (all units of a level in one launch, solved in place in shared memory)" if any(inv_chain_flags) else ""),
-                    sum(1 if c else lv.n_units for lv, c in zip(lvls, inv_chain_flags)), 8 * elems),
+                    sum(-(-lv.n_units // c) if c else lv.n_units for lv, c in zip(lvls, inv_chain_flags)), 8 * elems),
     }
     pm = dict(zip(HotPathRunner.PHASES, phase_ms))
     dom = max(phase_info, key=lambda p: pm[p])

@@ -206,7 +206,7 @@ class HotPathRunner:
             nb = _native.backward_weight_batched_workspace_bytes(batch, 4, lv.cq, lv.height, lv.width, *lv.kernel_size,
                                                                  lv.n_units - 1) if (c and batched_wgrad and lv.n_units > 2) else 0
             self.wg_batched.append(torch.zeros(nb, dtype=torch.uint8, device=self.device) if nb else None)
-        self.inv_chain = [False] * len(stack.levels)   # decided by _probe_inverse_chain() once the tables exist
+        self.inv_chain = [0] * len(stack.levels)   # units per inverse-chain launch: _probe_inverse_chain(), once the tables exist
         self._want_inv_chain = chain
         # level_parallel: the levels of a FincStack have independent inputs, so their unit chains (forward,
         # dX, inverse) may run next to each other -- one stream per level, forked from and joined to the
@@ -491,11 +491,18 @@ class HotPathRunner:
         if self.device_latents:
             s.zin[li].normal_()
         if self.inv_chain[li] and li not in self.dense:
-            # the whole sampling chain of the level: ONE launch, tiles stay in shared memory, no intermediate written
-            out = s.samp[li][(lv.n_units - 1) % 2]
-            _native.inverse_chain(s.zin[li], self.tables[li][_native.PREP_INVERSE], lv.kernel_size,
-                                  range(lv.n_units - 1, -1, -1), out=out)
-            s.sample_out[li] = out
+            # the sampling chain of the level in sub-chains of `m` units (m = all of them when their tables fit shared
+            # memory together): one launch each, tiles stay in shared memory, nothing written in between
+            m, U = self.inv_chain[li], lv.n_units
+            n_chunks = (U + m - 1) // m
+            final = (U - 1) % 2                            # the buffer the per-unit path ends in (the out-slab view)
+            src, cur, hi = s.zin[li], (final - (n_chunks - 1)) % 2, U - 1
+            for _ in range(n_chunks):
+                lo = max(hi - m + 1, 0)
+                _native.inverse_chain(src, self.tables[li][_native.PREP_INVERSE], lv.kernel_size,
+                                      range(hi, lo - 1, -1), out=s.samp[li][cur])
+                src, cur, hi = s.samp[li][cur], cur ^ 1, lo - 1
+            s.sample_out[li] = src
             return
         src, cur = s.zin[li], 0
         for u in reversed(range(lv.n_units)):
@@ -529,21 +536,25 @@ class HotPathRunner:
             torch.cuda.synchronize(self.device)
 
     def _probe_inverse_chain(self):
-        """which levels' sampling chains run as one finc_inverse_chain_f32 launch (register-window shapes whose
-        unit tables fit shared memory together); the others keep one launch per unit"""
-        self.inv_chain = [False] * len(self.stack.levels)
+        """per level: how many units one finc_inverse_chain_f32 launch solves (0 = the shape is not covered by the
+        register-window kernel: one launch per unit).  All units when their tables fit shared memory together,
+        otherwise the largest sub-chain that does."""
+        self.inv_chain = [0] * len(self.stack.levels)
         if not self._want_inv_chain or self.tables is None:
             return
         s = self.slots[0]
         for li, lv in enumerate(self.stack.levels):
-            if lv.n_units < 2:
-                continue
-            try:
-                _native.inverse_chain(s.zin[li], self.tables[li][_native.PREP_INVERSE], lv.kernel_size,
-                                      range(lv.n_units - 1, -1, -1), out=s.samp[li][(lv.n_units - 1) % 2])
-                self.inv_chain[li] = True
-            except _native.FincNativeError:
-                pass
+            U = lv.n_units
+            for m in sorted({U, (U + 1) // 2, (U + 2) // 3, (U + 3) // 4, 8, 4, 2}, reverse=True):
+                if m < 2 or m > U:
+                    continue
+                try:
+                    _native.inverse_chain(s.zin[li], self.tables[li][_native.PREP_INVERSE], lv.kernel_size,
+                                          range(U - 1, U - 1 - m, -1), out=s.samp[li][(U - 1) % 2])
+                    self.inv_chain[li] = m
+                    break
+                except _native.FincNativeError:
+                    pass
 
     def _prepare_warm_and_capture(self):
         self._prepare_weights()

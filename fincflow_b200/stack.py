@@ -258,10 +258,14 @@ class HotPathRunner:
             for lv in stack.levels:
                 nb = [_native.prepared_weights_bytes(kind, batch, 4, lv.cq, lv.height, lv.width, *lv.kernel_size)
                       for kind in (_native.PREP_FORWARD, _native.PREP_BACKWARD_INPUT, _native.PREP_INVERSE)]
-                if min(nb) == 0:
-                    tabs = None
-                    break
-                tabs.append([torch.empty((lv.n_units, n), dtype=torch.uint8, device=self.device) for n in nb])
+                li = len(tabs)
+                # a chained level stages the raw weights itself: only its inverse table is needed
+                need = [k for k in range(3) if not (self.chain[li] and k != _native.PREP_INVERSE)]
+                if min(nb[k] for k in need) == 0:
+                    tabs.append(None)               # this level re-stages the raw weights in every launch
+                    continue
+                tabs.append([torch.empty((lv.n_units, nb[k]), dtype=torch.uint8, device=self.device) if k in need else None
+                             for k in range(3)])
             self.tables = tabs
         self.slots = [_Slot(stack, batch, self.device, host_io) for _ in range(slots)]
         self.graphs = [None] * slots
@@ -316,6 +320,8 @@ class HotPathRunner:
         fork.record(main)
         k = 0
         for li, lv in enumerate(st.levels):
+            if self.tables[li] is None:
+                continue
             o = st.offsets[li][0]
             w_units = st.flat.detach()[o:o + lv.n_units * lv.unit_numel].view(lv.n_units, 4 * lv.cq, lv.cq, *lv.kernel_size)
             for kind in range(3):
@@ -361,7 +367,7 @@ class HotPathRunner:
 
     def _w(self, li, u, kind):
         """keyword arguments selecting the raw weights or the prepared table of unit (li, u)"""
-        if self.tables is None:
+        if self.tables is None or self.tables[li] is None:
             return dict(w=self.stack.unit_weight(li, u).detach())
         return dict(w=None, prepared=self.tables[li][kind][u], ksize=self.stack.levels[li].kernel_size)
 
@@ -545,6 +551,8 @@ class HotPathRunner:
         s = self.slots[0]
         for li, lv in enumerate(self.stack.levels):
             U = lv.n_units
+            if self.tables[li] is None:
+                continue
             for m in sorted({U, (U + 1) // 2, (U + 2) // 3, (U + 3) // 4, 8, 4, 2}, reverse=True):
                 if m < 2 or m > U:
                     continue

@@ -569,7 +569,7 @@ class FastFlowStep(_Chain):
         unit, glow = self.fastflow_step.fastflow_unit, self.fastflow_step.glow_unit
         act = getattr(glow.glow_step, "actnorm", None)
         if (self.fused and glow.fused and not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32
-                and (act is None or act.is_initialized())
+                and (act is None or act.is_initialized()) and x.is_contiguous() and x.data_ptr() % 16 == 0
                 and _native.chain_supported(4, unit.cq, x.shape[2], x.shape[3], unit.kernel_size, True)):
             # z = FInC(x) never leaves shared memory: y = A z + b is written, then the coupling layer
             A, b, ld_pix, _, _ = _glue_constants(glow)
@@ -578,7 +578,7 @@ class FastFlowStep(_Chain):
                 if b is None or b.device != x.device:
                     b = self._zero_bias = torch.zeros(A.shape[0], device=x.device)
             H, W = x.shape[2], x.shape[3]
-            y = _native.chain(x.contiguous(), unit.weight.detach().unsqueeze(0), torch.empty_like(x),
+            y = _native.chain(x, unit.weight.detach().unsqueeze(0), torch.empty_like(x),
                               A=A.unsqueeze(0), bias=b.unsqueeze(0))
             y, ld = glow.glow_step.coupling(y)
             ld = ld + (H * W) * ld_pix

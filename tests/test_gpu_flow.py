@@ -355,4 +355,10 @@ def test_fastflowstep_fused_eval_equals_layer_by_layer(actnorm):
                 flows.FastFlowStep.fused = True
         assert fused_launches == ref_launches - 1
         assert rel_err(y.cpu().numpy(), y_ref.cpu().numpy()) <= 2e-6
+        with torch.no_grad():   # a view the chain kernel cannot take (not 16-byte aligned): the layer-by-layer path runs
+            flat = torch.randn(x.numel() + 1, device="cuda")
+            xv = flat[1:].view_as(x)
+            xv.copy_(x)
+            y2, ld2 = step(xv)
+        assert rel_err(y2.cpu().numpy(), y_ref.cpu().numpy()) <= 2e-6 and rel_err(ld2.cpu().numpy(), ld_ref.cpu().numpy()) <= 1e-6
         assert rel_err(ld.cpu().numpy(), ld_ref.cpu().numpy()) <= 1e-6

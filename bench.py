@@ -741,8 +741,11 @@ def main_ours(args):
                 "algorithmic_bytes_per_launch": bytes_phase // nlaunch, "peak_source": peak_src,
                 "all_phases": {p: {"ms": round(pm[p], 4), "frac": round(phase_info[p][2] / (pm[p] * 1e-3) / 1e9 / peak, 4)}
                                for p in phase_info},
-                "note": "batch-256 launches move 1.6-6.3 MB each (<1 us at peak): launch/latency-bound; "
-                        "see `kernels` for the same kernels streaming from HBM at batch 16384"}
+                "note": "algorithmic bytes count every unit (SURVEY 8d: 8 B per element and unit, 12 for backward) although a "
+                        "chain launch keeps the 16 units of a level in shared memory and touches DRAM for one tensor "
+                        "(`traffic`); batch-256 work is bound by dependent wavefront latency (inverse: 16 units x 31 steps per "
+                        "tile) and instruction issue (forward / dX chains), not by HBM: see `kernels` for the per-unit "
+                        "kernels streaming from HBM at batch 16384"}
 
     extras = None
     whole = None

@@ -389,12 +389,31 @@ def kernel_detail(torch, _native, dev, peak):
             flops = 2.0 * B * H * W * CT * (CT // 4) * KSIZE * KSIZE
             t_roof_us = max(nbytes / peak / 1e3, flops / ffma / 1e6)
             bound = "hbm" if nbytes / peak / 1e3 >= flops / ffma / 1e6 else "fp32"
+            units_of = {}
+            if B == PER_GPU_BATCH:   # the round-2 launches of the step: all 16 units of a level per launch
+                U = UNITS_PER_LEVEL
+                wU = torch.stack([FastFlowUnit(CT, CT, (KSIZE, KSIZE)).weight.detach() for _ in range(U)]).to(dev).contiguous()
+                actsU = torch.empty(U, B, CT, H, W, device=dev)
+                dzU = torch.randn(U + 1, B, CT, H, W, device=dev)
+                dwU = torch.empty_like(wU)
+                tabU = torch.empty((U, tabs[_native.PREP_INVERSE].shape[1]), dtype=torch.uint8, device=dev)
+                _native.prepare_weights(wU, tabU, _native.PREP_INVERSE, B, H, W)
+                wsU = torch.zeros(_native.backward_weight_batched_workspace_bytes(B, 4, CT // 4, H, W, KSIZE, KSIZE, U - 1),
+                                  dtype=torch.uint8, device=dev)
+                fns.update({
+                    "forward chain (16 units / launch, all activations written)": lambda: _native.chain(x, wU, actsU),
+                    "backward-data chain (15 units / launch)": lambda: _native.chain(dzU[U], wU, dzU[:U], units=range(U - 1, 0, -1), transpose=True),
+                    "backward_weight batched (15 units / launch)": lambda: _native.backward_weight_batched(dzU[2:], actsU[:U - 1], dwU[1:], kk, workspace=wsU),
+                    "inverse chain (16 units / launch, in place in shared memory)": lambda: _native.inverse_chain(x, tabU, kk, range(U - 1, -1, -1), out=y),
+                })
+                units_of = {"forward chain": U, "backward-data chain": U - 1, "backward_weight batched": U - 1, "inverse chain": U}
             for name, fn in fns.items():
+                mult = next((v for k, v in units_of.items() if name.startswith(k)), 1)
                 if name.startswith("affine1x1"):
                     k_flops, k_roof, k_bound = 2.0 * B * H * W * CT * CT, None, "hbm"
                     k_roof = max(nbytes / peak / 1e3, k_flops / ffma / 1e6)
                 else:
-                    k_flops, k_roof, k_bound = flops, t_roof_us, bound
+                    k_flops, k_roof, k_bound = flops * mult, t_roof_us * mult, bound
                 # a CUDA graph of CHAIN launches (what the step replays), L2 flushed before each replay;
                 # at batch 256 the launches of a chain find their operands in L2, as inside the step
                 CHAIN = 8
@@ -418,8 +437,9 @@ def kernel_detail(torch, _native, dev, peak):
                     ts.append(e0.elapsed_time(e1) / CHAIN)
                 del g
                 us = 1e3 * statistics.median(ts)
-                out.append({"kernel": name, "shape": [B, CT, H, W], "us": round(us, 2),
-                            "GBps": round(nbytes / us / 1e3, 1), "frac_of_hbm_peak": round(nbytes / us / 1e3 / peak, 3),
+                out.append({"kernel": name, "shape": [B, CT, H, W], "units_per_launch": mult, "us": round(us, 2),
+                            "us_per_unit": round(us / mult, 2),
+                            "GBps": round(mult * nbytes / us / 1e3, 1), "frac_of_hbm_peak": round(mult * nbytes / us / 1e3 / peak, 3),
                             "TFLOPs": round(k_flops / us / 1e6, 2), "bound": k_bound,
                             "frac_of_roofline": round(k_roof / us, 3), "images_per_s": round(B / us * 1e6)})
             del x, dz, y

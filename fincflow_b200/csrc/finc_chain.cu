@@ -9,7 +9,7 @@
 //     cur = x[block]                                   (one TMA bulk load: the block is contiguous)
 //     for unit u in order:   nxt = FInC_u(cur)         (conv_sub of finc_conv.cuh, shared memory -> shared memory)
 //                            [nxt = A_u nxt + b_u]     (the Glow glue of fastflow_cifar_multi_gpu.py:238-256)
-//                            y[u][block] = nxt         (one TMA bulk store, overlapped with the next unit)
+//                            y[u][block] = nxt         (coalesced 128-bit stores by all threads; ping-pong buffers)
 //
 // Uses: (1) FastFlowStep inference: FastFlowUnit + ActNorm + Conv1x1 = ONE launch (n_units = 1, affine given;
 // reference: fastflow/fastflow.py:31-50, layers/actnorm.py:14-52, layers/conv1x1.py:18-43);
@@ -51,8 +51,6 @@ struct ChainArgs {
     int n_blocks;
     int wk_floats;        // staged weight table of one unit (all groups)
 };
-
-__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // raw weights per thread kept in registers between the prefetch and the table write
 template <int CT>

@@ -105,6 +105,8 @@ class FastFlowUnit(nn.Module):
 
     def forward(self, x, context=None):
         want = self.logdet_mode == "tensor"
+        if torch.is_grad_enabled() and self.weight.requires_grad:
+            self._dense_key = None   # a training forward: the dense-inverse table may be stale after the next update
         z, logdet = finc_conv(x, self.weight, 4, _native.ORDERS_UNIT, self.mask_in_backward, want)
         return z, (logdet if want else 0.0)  # reference: 0.0 + 0.0 + 0.0 + 0.0 (fastflow.py:34-50)
 

@@ -236,13 +236,16 @@ class Coupling(FlowLayer):
         return (self.tensor_core and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
                 and _native.coupling_prepared_bytes(self.n_channels, self.width) > 0)
 
-    def prepared(self, with_backward=False):
-        """hi / lo split weight blob, rebuilt only when a parameter changed (in-place updates bump
-        `_version`; optimizers and load_state_dict do).  `with_backward` adds the transposed weights of
-        the backward pass."""
+    def prepared(self, with_backward=False, training=False):
+        """hi / lo split weight blob.  Evaluation (no_grad) reuses it while no parameter changed: the cache is
+        keyed on (data_ptr, `_version`) of every parameter -- in-place updates, load_state_dict and most optimizers
+        bump `_version`.  torch.optim.Adam(fused=True) does NOT (measured: version 0 -> 0 after step()), so a
+        training forward (`training=True`) never trusts the cache: it always rebuilds the blob and leaves the
+        cache invalid, and the first evaluation after an optimizer step rebuilds it once more.  `with_backward`
+        adds the transposed weights of the backward pass."""
         ps = self._params()
-        key = (with_backward,) + tuple((p.data_ptr(), p._version) for p in ps)
-        if self._blob is None or key != self._blob_key or self._blob.device != ps[0].device:
+        key = None if training else (with_backward,) + tuple((p.data_ptr(), p._version) for p in ps)
+        if training or self._blob is None or key != self._blob_key or self._blob.device != ps[0].device:
             self._blob = _native.coupling_prepare(*[p.detach() for p in ps], self.net[4].logscale_factor,
                                                   out=self._blob if self._blob is not None
                                                   and self._blob.device == ps[0].device else None,
@@ -291,7 +294,7 @@ class _CouplingFn(torch.autograd.Function):
         ws = None
         if ctx.native:
             ws = torch.empty(_native.coupling_workspace_bytes(B, C, H, W, module.width), dtype=torch.uint8, device=x.device)
-        blob = module.prepared(with_backward=ctx.native)
+        blob = module.prepared(with_backward=ctx.native, training=train)
         y, logdet = _native.coupling_apply(x, blob, module.width, flags=module._flags(), workspace=ws)
         ctx.save_for_backward(x)
         ctx.ws, ctx.blob = ws, blob
@@ -534,6 +537,8 @@ def _fused_glow_forward(self, x):
         y = _native.affine1x1(x.contiguous(), A, b)
         y, ld = gs.coupling(y)
         return y, ld + (H * W) * ld_pix
+    self._glue_key = None   # training forward: the cached evaluation constants may not be trusted afterwards
+                            # (torch's fused Adam updates parameters without bumping their version counters)
     A, b = affine_of(act, conv)
     y = _Affine1x1Fn.apply(x, A, b)
     ld_w = conv.__dict__.pop("_ld_batched", None)     # set by FastFlow.forward: one batched LU per level

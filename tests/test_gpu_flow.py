@@ -362,3 +362,48 @@ def test_fastflowstep_fused_eval_equals_layer_by_layer(actnorm):
             y2, ld2 = step(xv)
         assert rel_err(y2.cpu().numpy(), y_ref.cpu().numpy()) <= 2e-6 and rel_err(ld2.cpu().numpy(), ld_ref.cpu().numpy()) <= 1e-6
         assert rel_err(ld.cpu().numpy(), ld_ref.cpu().numpy()) <= 1e-6
+
+
+def test_flat_adam_matches_torch_adam_and_caches_see_graph_updates():
+    """FlowTrainer's one-launch Adam over the flattened parameters follows torch.optim.Adam, and an evaluation after
+    CUDA-graph training steps sees the trained weights (version counters are bumped after every replay: the layers'
+    prepared-weight caches are keyed on them)"""
+    from fincflow_b200 import flows
+    from fincflow_b200.train import FlowTrainer
+
+    def run(**kw):
+        torch.manual_seed(5)
+        m = flows.FastFlow(n_blocks=2, block_size=2, image_size=(3, 16, 16), actnorm=True, width=128).cuda()
+        tr = FlowTrainer(m, lr=1e-3, **kw)
+        m.preprocess.layers[0].fixed_noise = torch.full((8, 3, 16, 16), 0.5, device="cuda")
+        g = torch.Generator(device="cuda").manual_seed(9)
+        xs = [torch.randint(0, 256, (8, 3, 16, 16), device="cuda", generator=g).float() for _ in range(6)]
+        losses = [float(tr.step(x)) for x in xs]
+        m.eval()
+        with torch.no_grad():
+            _, logp = m(xs[0])
+        return losses, [p.detach().clone() for p in m.parameters()], logp.clone(), tr
+
+    l_t, p_t, lp_t, tr_t = run(flat_adam=False)
+    l_f, p_f, lp_f, tr_f = run(flat_adam=True)
+    # the same training with the coupling layers on PyTorch's own convolutions (fp32): an implementation whose
+    # weight caches survive an optimizer step (torch's fused Adam does not bump `_version`) fails here at step 2
+    flows.Coupling.tensor_core = False
+    try:
+        l_ref = run(flat_adam=False)[0]
+    finally:
+        flows.Coupling.tensor_core = True
+    assert np.allclose(l_t, l_ref, rtol=1e-4) and np.allclose(l_f, l_ref, rtol=1e-4), (l_t, l_f, l_ref)
+    l_g, p_g, lp_g, tr_g = run(flat_adam=True, use_graph=True, graph_warmup=2)
+    assert type(tr_t.optimizer).__name__ == "Adam" and type(tr_f.optimizer).__name__ == "FlatAdam"
+    assert tr_g._graph is not None
+    assert np.allclose(l_t, l_f, rtol=1e-5) and np.allclose(l_f, l_g, rtol=1e-4)
+    for a, b, c in zip(p_t, p_f, p_g):
+        assert rel_err(b.cpu().numpy(), a.cpu().numpy()) <= 1e-5
+        assert rel_err(c.cpu().numpy(), b.cpu().numpy()) <= 1e-4
+    # evaluation after training: the graph run must not evaluate with weights cached before its last updates
+    assert rel_err(lp_f.cpu().numpy(), lp_t.cpu().numpy()) <= 1e-5
+    assert rel_err(lp_g.cpu().numpy(), lp_f.cpu().numpy()) <= 1e-4
+    sd = tr_f.optimizer.state_dict()
+    tr_g.optimizer.load_state_dict(sd)
+    assert torch.equal(tr_g.optimizer.exp_avg, tr_f.optimizer.exp_avg) and float(tr_g.optimizer.step_t) == 6.0

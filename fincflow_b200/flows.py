@@ -575,6 +575,7 @@ class FastFlowStep(_Chain):
         act = getattr(glow.glow_step, "actnorm", None)
         if (self.fused and glow.fused and not torch.is_grad_enabled() and x.is_cuda and x.dtype == torch.float32
                 and (act is None or act.is_initialized()) and x.is_contiguous() and x.data_ptr() % 16 == 0
+                and unit.weight.data_ptr() % 16 == 0 and unit.weight.is_contiguous()
                 and _native.chain_supported(4, unit.cq, x.shape[2], x.shape[3], unit.kernel_size, True)):
             # z = FInC(x) never leaves shared memory: y = A z + b is written, then the coupling layer
             A, b, ld_pix, _, _ = _glue_constants(glow)

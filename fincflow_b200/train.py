@@ -96,16 +96,21 @@ class FlowTrainer:
     # ---- flat gradient buffer + buckets -----------------------------------------------------------
     def _build_buckets(self, bucket_mb):
         dev, dt = self.params[0].device, self.params[0].dtype
-        total = sum(p.numel() for p in self.params)
-        self.flat_grad = torch.zeros(total, dtype=dt, device=dev)
-        # offsets in REVERSE parameter order: the last layers' gradients are ready first
+        # offsets in REVERSE parameter order: the last layers' gradients are ready first.  Every parameter starts on
+        # a 64-byte boundary (the flat parameter buffer uses the same layout, and the kernels' vector loads / TMA
+        # copies need 16-byte aligned weights)
+        ALIGN = 16
         self.offsets = {}
         off = 0
         order = list(reversed(self.params))
         for p in order:
             self.offsets[p] = off
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        total = off
+        self.flat_grad = torch.zeros(total, dtype=dt, device=dev)
+        for p in order:
+            off = self.offsets[p]
             p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
         limit = max(int(bucket_mb * 1024 * 1024 / self.flat_grad.element_size()), 1)
         self.buckets, start, members = [], 0, []
         for p in order:
@@ -125,7 +130,7 @@ class FlowTrainer:
 
     def _make_flat_adam(self, lr):
         """parameters become views into ONE flat buffer laid out like the flat gradient buffer"""
-        self.flat_param = torch.empty_like(self.flat_grad)
+        self.flat_param = torch.zeros_like(self.flat_grad)
         for p in self.params:
             o = self.offsets[p]
             view = self.flat_param[o:o + p.numel()].view_as(p)
